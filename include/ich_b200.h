@@ -1,0 +1,109 @@
+/* libich_b200.so -- C ABI of the B200-native U-Net hot path.
+ *
+ * The reference (antoine-spahr/Label-Efficient-Volumetric-Deep-Semantic-Segmentation-of-ICH) is pure Python/PyTorch and
+ * has no FFI of its own; the operators below are what its nn.Module / loss-module hot path dispatches to inside
+ * PyTorch (cuDNN / ATen).  Each entry point names the reference call site (relative to code/src/) it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch's caching allocator); the library never allocates;
+ *   - activations are channel-last rows [voxel][channel] with an explicit channel pitch `*_ld` (elements), so a tensor
+ *     may be a channel slab of a wider (concat) buffer; `dtype` selects the activation element type;
+ *   - grids are (N, D, H, W); 2-D nets pass D = 1 and KD = 1 / FD = 1;
+ *   - `stream` is a cudaStream_t; all work is enqueued asynchronously on it;
+ *   - return 0 on success; non-zero on error, message via ich_last_error() (thread-local).
+ */
+#ifndef ICH_B200_H
+#define ICH_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICH_F32 0
+#define ICH_BF16 1
+
+const char* ich_last_error(void);
+int ich_abi_version(void);
+
+/* ---- layout: reference tensors are NC(D)HW fp32 (models/optim/UNet2D.py:137); the engine is N(D)HWC ------------- */
+int ich_layout_nc_to_nl(const float* src, void* dst, int dtype, int N, int C, long long S, int dst_ld, void* stream);
+int ich_layout_nl_to_nc(const void* src, int dtype, int src_ld, float* dst, int N, int C, long long S, void* stream);
+
+/* ---- convolution, "same" padding, stride 1: nn.Conv3d/Conv2d k3 p1 (models/networks/UNet.py:153,155,158,160) and the 1x1
+ *      heads (:84, :228).  wpack = [taps*Cin][Cout] fp32.  The data-gradient is the same entry point called with the
+ *      flipped/transposed pack.  CUDA-core fp32-accumulate path (fp32 verification mode + odd shapes).               */
+int ich_conv_fwd(const void* x, int x_ld, const float* wpack, const float* bias, void* y, int y_ld, int dtype, int N, int D, int H,
+                 int W, int Cin, int Cout, int KD, int KH, int KW, int relu, void* stream);
+/* weight gradient in torch layout [Cout][Cin][KD*KH*KW] fp32 (autograd of the convs above) */
+int ich_conv_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, int dtype, float* dw, int N, int D, int H, int W, int Cin,
+                   int Cout, int KD, int KH, int KW, void* stream);
+
+/* ---- tcgen05 / TMEM / TMA implicit-GEMM convolution, bf16 operands, fp32 accumulate (same call sites as ich_conv_fwd).
+ *      wpack_bf16 = [taps][Cout][Cin] bf16 (K-major per tap).  Requires Cin % 16 == 0, Cout % 16 == 0, Cout <= 256.
+ *      ich_conv_tc_supported() returns 1 when the shape is eligible.                                                  */
+int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
+int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
+                    int Cin, int Cout, int KD, int KH, int KW, int relu, void* stream);
+/* weight gradient on tensor cores; dw in torch layout [Cout][Cin][taps] fp32; workspace: see ich_conv_tc_wgrad_workspace */
+int ich_conv_tc_wgrad_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
+int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout,
+                      int KD, int KH, int KW, void* stream);
+
+/* ---- transposed conv k2 s2: nn.ConvTranspose3d/2d (models/networks/UNet.py:75-76). Grid args = the COARSE grid;
+ *      FD = depth factor (2 for 3-D, 1 for 2-D). wpack = [Cin][taps*Cout], wpack_d = [taps*Cout][Cin], taps = 4*FD.     */
+int ich_convT2_fwd(const void* x, int x_ld, const float* wpack, const float* bias, void* y, int y_ld, int dtype, int N, int D, int H,
+                   int W, int Cin, int Cout, int FD, void* stream);
+int ich_convT2_dgrad(const void* dy, int dy_ld, const float* wpack_d, void* dx, int dx_ld, int dtype, int N, int D, int H, int W, int Cin,
+                     int Cout, int FD, void* stream);
+int ich_convT2_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, int dtype, float* dw, int N, int D, int H, int W, int Cin, int Cout,
+                     int FD, void* stream);
+
+/* ---- BatchNorm (+ReLU): nn.BatchNorm3d/2d + nn.ReLU (models/networks/UNet.py:149,154,156,159,161,173-174) ----------- */
+int ich_colstats(const void* x, int ld, int dtype, long long M, int C, double* sum, double* sumsq, void* stream);
+int ich_bn_finalize(const double* sum, const double* sumsq, long long count, int C, const float* gamma, const float* beta,
+                    const float* conv_bias, float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                    float* save_mean, float* save_invstd, int training, void* stream);
+int ich_affine_act(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C, int relu,
+                   void* stream);
+int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                   const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype, long long M, int C, int relu,
+                   int training, void* stream);
+
+/* ---- nn.MaxPool3d/2d(2,2) (models/networks/UNet.py:82,109); grid args = the INPUT grid ------------------------------ */
+int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
+int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W, int C,
+                     int FD, void* stream);
+
+/* ---- torch.cat([res, x], 1) (models/networks/UNet.py:119) as channel-slab copies; AdaptiveAvgPool(1) (:295,318) ------ */
+int ich_slab_copy(const void* src, int src_ld, void* dst, int dst_ld, int dtype, long long M, int C, void* stream);
+int ich_avgpool_fwd(const void* x, int ld, int dtype, float* out, int N, long long S, int C, void* stream);
+int ich_avgpool_bwd(const float* dout, void* dx, int ld, int dtype, int N, long long S, int C, void* stream);
+
+/* ---- final 1x1 conv + Sigmoid / Softmax (models/networks/UNet.py:84-91,122); act: 0 none, 1 sigmoid, 2 softmax -------- */
+int ich_head_fwd(const void* x, int x_ld, int dtype, const float* w, const float* b, float* out, int N, long long S, int Cin, int Cout, int act,
+                 void* stream);
+int ich_head_dlogit(const float* out, const float* dout, void* dl, int dtype, int N, long long S, int Cout, int act, void* stream);
+int ich_head1_bwd(const void* x, int x_ld, int dtype, const float* w, const float* out, const float* dout, void* dx, int dx_ld, float* dw,
+                  float* db, long long M, int Cin, int act, void* stream);
+
+/* ---- BinaryDiceLoss / ComboLoss (models/optim/LossFunctions.py:39-63,143-166) ---------------------------------------- */
+int ich_seg_loss_fwd(const float* pred, const float* mask, int B, long long S, float P, float eps, float alpha_empty, float w_bce, float w_dice,
+                     float beta, int reduction, double* acc, float* per_sample, float* loss, void* stream);
+int ich_seg_loss_bwd(const float* pred, const float* mask, const double* acc, const float* gscale, int B, long long S, float P, float eps,
+                     float alpha_empty, float w_bce, float w_dice, float beta, float* dpred, void* stream);
+
+/* ---- InfoNCELoss / LocalInfoNCELoss (models/optim/LossFunctions.py:208-230,308-341) ----------------------------------- */
+int ich_infonce_fwd(const float* P, int B, int R, int E, float tau, float* Pn, float* invn, float* lse, float* rowloss, float* loss,
+                    unsigned int* counter, void* stream);
+int ich_infonce_bwd(const float* Pn, const float* invn, const float* lse, int B, int R, int E, float tau, const float* gout, float* dP,
+                    void* stream);
+int ich_region_gather(const float* f, const int* corners, float* P, int bs, int H, int W, int C, int A, int K, int view, void* stream);
+int ich_region_scatter(const float* dP, const int* corners, float* df, int bs, int H, int W, int C, int A, int K, int view, void* stream);
+
+/* ---- batch_binary_confusion_matrix (utils/tensor_utils.py:12-36) with the >= 0.5 threshold of models/optim/UNet2D.py:220 -- */
+int ich_confusion(const float* pred, const float* target, int B, long long S, float thr, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

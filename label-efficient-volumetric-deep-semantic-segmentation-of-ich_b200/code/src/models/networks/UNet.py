@@ -1,0 +1,255 @@
+"""B200-native drop-in for the reference's `src.models.networks.UNet` module.
+
+Same classes, constructor signatures, attribute tree and state-dict keys as the reference
+(/root/reference/code/src/models/networks/UNet.py: UNet :18-127, ConvBlock :129-177, MLPHead :179-209,
+ConvHead :211-243, UNet_Encoder :245-326, Partial_UNet :328-435), so the reference trainers
+(`UNet2D`, `Contrastive`, ...) and scripts run on top of it unchanged.  The parameters live in ordinary
+nn.Conv/BatchNorm/ConvTranspose/Linear sub-modules (state-dict compatible in both directions), but `forward` never
+calls them: every arithmetic step runs in the hand-written sm_100a kernels of libich_b200.so through
+`ich_b200.ops` (channel-last bf16/fp32 activations, tcgen05 implicit-GEMM convs).  CUDA only -- no CPU fallback.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+from ich_b200 import ops  # noqa: E402
+
+
+def _dropout_list(p_dropout, depth):
+    """Reference validation of the p_dropout argument (UNet.py:47-53)."""
+    if isinstance(p_dropout, float):
+        return [p_dropout] * depth
+    if isinstance(p_dropout, list):
+        assert len(p_dropout) == depth, (f'p_dropout provided as list should have the same length as depth. '
+                                         f'p_dropout {len(p_dropout)} vs depth {depth}.')
+        return p_dropout
+    raise TypeError(f'p_dropout list not supported. Should be float or list of float. Given {type(p_dropout)}.')
+
+
+def _filters(in_channels, top_filter, depth):
+    """Filter plan of UNet.py:61-63."""
+    down = [(in_channels, top_filter)] + [(top_filter * 2 ** d, top_filter * 2 ** (d + 1)) for d in range(depth - 2)]
+    bottleneck = (top_filter * 2 ** (depth - 2), top_filter * 2 ** (depth - 1))
+    return down, bottleneck
+
+
+def _not_built(what):
+    raise NotImplementedError(f'ich_b200: {what} is not part of the B200 hot path yet (SURVEY section 8f); '
+                              f'refusing to fall back silently')
+
+
+class ConvBlock(nn.Module):
+    """[Conv k3 p1 -> BatchNorm -> ReLU] x 2 (+ Dropout if p > 0). Reference: UNet.py:129-177."""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None, kernel_size=3, use_3D=False, p_dropout=0.0):
+        super(ConvBlock, self).__init__()
+        assert 0.0 <= p_dropout <= 1.0, f'Dropout probaility must be in [0.0, 1.0]. Given {p_dropout}.'
+        self.activation = nn.ReLU()
+        self.dropout = nn.Dropout(p=p_dropout)
+        mid_channels = mid_channels if mid_channels else out_channels
+        conv = nn.Conv3d if use_3D else nn.Conv2d
+        bn = nn.BatchNorm3d if use_3D else nn.BatchNorm2d
+        self.conv1 = conv(in_channels=in_channels, out_channels=mid_channels, kernel_size=kernel_size, padding=1)
+        self.bn1 = bn(mid_channels)
+        self.conv2 = conv(in_channels=mid_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1)
+        self.bn2 = bn(out_channels)
+
+    def _unit(self, x, conv, bn):
+        if conv.padding[0] * 2 + 1 != conv.kernel_size[0]:
+            _not_built(f'kernel_size={conv.kernel_size} with padding={conv.padding}')
+        training = self.training or not bn.track_running_stats
+        z = ops.ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, True)
+        if training and bn.track_running_stats:
+            bn.num_batches_tracked += 1
+        return z
+
+    def forward_cl(self, x):
+        """Channel-last engine path: x [N, D, H, W, C] in the engine dtype."""
+        x = self._unit(x, self.conv1, self.bn1)
+        x = self._unit(x, self.conv2, self.bn2)
+        if self.dropout.p > 0.0 and self.training:
+            x = self.dropout(x)      # elementwise, RNG-dependent: torch's Philox dropout on the engine tensor
+        return x
+
+    def forward(self, input):
+        was_4d = input.dim() == 4
+        return ops.from_channels_last(self.forward_cl(ops.to_channels_last(input)), was_4d)
+
+
+class MLPHead(nn.Module):
+    """Linear/ReLU projection head (no ReLU after the last layer). Reference: UNet.py:179-209. B x 256 inputs: plain library
+    GEMMs (cuBLAS via nn.Linear) -- negligible next to the encoder."""
+
+    def __init__(self, Neurons_layer=[512, 256, 128]):
+        nn.Module.__init__(self)
+        self.fc_layers = nn.ModuleList(nn.Linear(in_features=n_in, out_features=n_out)
+                                       for n_in, n_out in zip(Neurons_layer[:-1], Neurons_layer[1:]))
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        for linear in self.fc_layers[:-1]:
+            x = self.relu(linear(x))
+        return self.fc_layers[-1](x)
+
+
+class ConvHead(nn.Module):
+    """1x1-conv/ReLU projection head. Reference: UNet.py:211-243."""
+
+    def __init__(self, channel_layer=[128, 256, 32], use_3D=False):
+        super(ConvHead, self).__init__()
+        conv = nn.Conv3d if use_3D else nn.Conv2d
+        self.conv_layers = nn.ModuleList(conv(in_channels=n_in, out_channels=n_out, kernel_size=1)
+                                         for n_in, n_out in zip(channel_layer[:-1], channel_layer[1:]))
+        self.relu = nn.ReLU()
+
+    def forward_cl(self, x):
+        n = len(self.conv_layers)
+        for i, conv in enumerate(self.conv_layers):
+            x = ops.ConvBias.apply(x, conv.weight, conv.bias, i < n - 1)
+        return x
+
+    def forward(self, x):
+        was_4d = x.dim() == 4
+        return ops.from_channels_last(self.forward_cl(ops.to_channels_last(x)), was_4d)
+
+
+class _UNetBase(nn.Module):
+    """Shared encoder / decoder plumbing of UNet, UNet_Encoder and Partial_UNet."""
+
+    def _build_encoder(self, depth, use_3D, in_channels, top_filter, midchannels_factor, p_dropout_list):
+        down, bottleneck = _filters(in_channels, top_filter, depth)
+        self.down_block = nn.ModuleList()
+        for ch, p in zip(down, p_dropout_list[:-1]):
+            self.down_block.append(ConvBlock(ch[0], ch[1], mid_channels=ch[1] // midchannels_factor, use_3D=use_3D, p_dropout=p))
+        return down, bottleneck
+
+    def _build_bottleneck(self, bottleneck, use_3D, midchannels_factor, p):
+        self.bottleneck_block = ConvBlock(bottleneck[0], bottleneck[1], mid_channels=bottleneck[1] // midchannels_factor, use_3D=use_3D,
+                                          p_dropout=p)
+        self.downpool = nn.MaxPool3d(kernel_size=2, stride=2) if use_3D else nn.MaxPool2d(kernel_size=2, stride=2)
+
+    def _build_decoder(self, up_filters, use_3D, bilinear):
+        self.up_samp = nn.ModuleList()
+        self.up_block = nn.ModuleList()
+        for ch in up_filters:
+            if bilinear:
+                self.up_block.append(ConvBlock(int(1.5 * ch[0]), ch[1], mid_channels=ch[1], use_3D=use_3D))
+                self.up_samp.append(nn.Upsample(scale_factor=2, mode='trilinear' if use_3D else 'bilinear', align_corners=True))
+            else:
+                self.up_block.append(ConvBlock(ch[0], ch[1], mid_channels=ch[1], use_3D=use_3D))
+                convT = nn.ConvTranspose3d if use_3D else nn.ConvTranspose2d
+                self.up_samp.append(convT(ch[0], ch[1], kernel_size=2, stride=2))
+
+    @property
+    def _fd(self):
+        return 2 if isinstance(self.downpool, nn.MaxPool3d) else 1
+
+    def _check_grid(self, x, n_pool):
+        f = 2 ** n_pool
+        d, h, w = x.shape[1:4]
+        if (self._fd == 2 and d % f) or h % f or w % f:
+            raise RuntimeError(f'ich_b200: spatial size {(d, h, w) if self._fd == 2 else (h, w)} must be divisible by {f} '
+                               f'(the reference has no pad/crop logic either, UNet.py:117-119)')
+
+    def _encode(self, x):
+        self._check_grid(x, len(self.down_block))
+        res = []
+        for block in self.down_block:                       # UNet.py:106-109
+            x = block.forward_cl(x)
+            res.append(x)
+            x = ops.MaxPool2.apply(x, self._fd)
+        return self.bottleneck_block.forward_cl(x), res     # UNet.py:112
+
+    def _decode(self, x, res):
+        for up, block, r in zip(self.up_samp, self.up_block, res[::-1]):     # UNet.py:117-119
+            if not isinstance(up, (nn.ConvTranspose3d, nn.ConvTranspose2d)):
+                _not_built('bilinear=True (nn.Upsample decoder)')
+            x = block.forward_cl(ops.UpConvCat.apply(x, r, up.weight, up.bias, self._fd))
+        return x
+
+
+class UNet(_UNetBase):
+    """2-D / 3-D U-Net. Reference: UNet.py:18-127."""
+
+    def __init__(self, depth=5, use_3D=False, bilinear=False, in_channels=1, out_channels=1, top_filter=64, midchannels_factor=2,
+                 p_dropout=0.5, use_final_activation=True):
+        super(UNet, self).__init__()
+        p_dropout_list = _dropout_list(p_dropout, depth)
+        self.return_bottleneck = False
+        down, bottleneck = self._build_encoder(depth, use_3D, in_channels, top_filter, midchannels_factor, p_dropout_list)
+        up_filters = [(top_filter * 2 ** d, top_filter * 2 ** (d - 1)) for d in range(depth - 1, 0, -1)]
+        self._build_decoder(up_filters, use_3D, bilinear)
+        self._build_bottleneck(bottleneck, use_3D, midchannels_factor, p_dropout_list[-1])
+        self.final_conv = nn.Conv3d(top_filter, out_channels, kernel_size=1) if use_3D else nn.Conv2d(top_filter, out_channels, kernel_size=1)
+        if use_final_activation:
+            self.final_activation = nn.Softmax(dim=1) if out_channels > 1 else nn.Sigmoid()
+        else:
+            self.final_activation = nn.Identity()
+
+    def forward(self, input):
+        was_4d = input.dim() == 4
+        x = ops.to_channels_last(input)
+        x, res = self._encode(x)
+        x_bottleneck = x
+        x = self._decode(x, res)
+        act = 0 if isinstance(self.final_activation, nn.Identity) else (2 if isinstance(self.final_activation, nn.Softmax) else 1)
+        out = ops.Head.apply(x, self.final_conv.weight, self.final_conv.bias, act)           # UNet.py:122
+        if was_4d:
+            out = out.squeeze(2)
+        if self.return_bottleneck:
+            return out, ops.from_channels_last(x_bottleneck, was_4d)
+        return out
+
+
+class UNet_Encoder(_UNetBase):
+    """U-Net encoder + global average pool + MLP head. Reference: UNet.py:245-326."""
+
+    def __init__(self, depth=5, use_3D=False, in_channels=1, MLP_head=[256, 128], top_filter=64, midchannels_factor=2, p_dropout=0.5):
+        super(UNet_Encoder, self).__init__()
+        p_dropout_list = _dropout_list(p_dropout, depth)
+        self.return_bottleneck = False
+        down, bottleneck = self._build_encoder(depth, use_3D, in_channels, top_filter, midchannels_factor, p_dropout_list)
+        self._build_bottleneck(bottleneck, use_3D, midchannels_factor, p_dropout_list[-1])
+        self.avg_pool = nn.AdaptiveAvgPool3d((1, 1, 1)) if use_3D else nn.AdaptiveAvgPool2d((1, 1))
+        self.mlp_head = MLPHead(Neurons_layer=[bottleneck[1]] + MLP_head)
+
+    def forward(self, input):
+        was_4d = input.dim() == 4
+        x, _ = self._encode(ops.to_channels_last(input))
+        pooled = ops.GlobalAvgPool.apply(x)                                     # UNet.py:318, fp32 [N, C]
+        out = self.mlp_head(pooled)                                             # UNet.py:321
+        if self.return_bottleneck:
+            return out, pooled.view(*pooled.shape, *([1, 1] if was_4d else [1, 1, 1]))
+        return out
+
+
+class Partial_UNet(_UNetBase):
+    """Full encoder, first n_decoder up-stages, ConvHead, no activation. Reference: UNet.py:328-435."""
+
+    def __init__(self, depth=5, n_decoder=3, use_3D=False, bilinear=False, in_channels=1, head_channel=[64, 32], top_filter=64,
+                 midchannels_factor=2, p_dropout=0.5):
+        super(Partial_UNet, self).__init__()
+        p_dropout_list = _dropout_list(p_dropout, depth)
+        self.return_bottleneck = False
+        down, bottleneck = self._build_encoder(depth, use_3D, in_channels, top_filter, midchannels_factor, p_dropout_list)
+        up_filters = [(top_filter * 2 ** d, top_filter * 2 ** (d - 1)) for d in range(depth - 1, depth - 1 - n_decoder, -1)]
+        self.n_decoder = n_decoder
+        self._build_decoder(up_filters, use_3D, bilinear)
+        self._build_bottleneck(bottleneck, use_3D, midchannels_factor, p_dropout_list[-1])
+        self.final_conv = ConvHead(channel_layer=[up_filters[-1][1]] + head_channel, use_3D=use_3D)
+
+    def forward(self, input):
+        was_4d = input.dim() == 4
+        x, res = self._encode(ops.to_channels_last(input))
+        x_bottleneck = x
+        x = self._decode(x, res[::-1][:self.n_decoder][::-1])                  # UNet.py:425-427
+        out = ops.from_channels_last(self.final_conv.forward_cl(x), was_4d)     # UNet.py:430
+        if self.return_bottleneck:
+            return out, ops.from_channels_last(x_bottleneck, was_4d)
+        return out

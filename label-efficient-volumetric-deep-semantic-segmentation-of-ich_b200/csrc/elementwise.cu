@@ -1,0 +1,541 @@
+// Bandwidth-bound kernels of the U-Net block: layout conversion, BatchNorm statistics / finalize / apply(+ReLU)
+// forward and backward, 2x max-pool forward / backward, channel-slab copies (skip concat), global average pool.
+// All activations are channel-last rows [M][C] with an explicit channel pitch `ld` so a tensor can be a channel slab
+// of a wider concat buffer.  Vector path: 16-byte accesses (8 bf16 / 4 fp32) when C, ld and the base are aligned.
+// Replaces ATen batch_norm / relu / max_pool3d / cat behind reference models/networks/UNet.py:82,119,149,154-161.
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+__host__ __device__ inline bool vec_ok(const void* p, int ld, int C) {
+  return (C % Vec<T>::N == 0) && (ld % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+inline int grid_for(long long work, int threads, int per_sm = 8) {
+  long long blocks = (work + threads - 1) / threads;
+  long long cap = (long long)ich_num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---- layout: NC(S) fp32 <-> N(S)C T --------------------------------------------------------------------------
+template <typename T>
+__global__ void nc_to_nl_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long long S, int ld) {
+  __shared__ float tile[32][33];
+  const long long s0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const long long n = blockIdx.z;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    long long s = s0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && s < S) ? src[(n * C + c) * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long s = s0 + i;
+    int c = c0 + threadIdx.x;
+    if (c < C && s < S) dst[(n * S + s) * ld + c] = from_f32<T>(tile[threadIdx.x][i]);
+  }
+}
+template <typename T>
+__global__ void nl_to_nc_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, long long S, int ld) {
+  __shared__ float tile[32][33];
+  const long long s0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const long long n = blockIdx.z;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long s = s0 + i;
+    int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && s < S) ? to_f32(src[(n * S + s) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    long long s = s0 + threadIdx.x;
+    if (c < C && s < S) dst[(n * C + c) * S + s] = tile[threadIdx.x][i];
+  }
+}
+// C == 1 fast path: a pure cast, fully coalesced.
+template <typename T>
+__global__ void cast_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f32<T>(src[i]);
+}
+template <typename T>
+__global__ void cast_to_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = to_f32(src[i]);
+}
+
+// ---- per-channel statistics over rows: sum and sum of squares -------------------------------------------------
+// Block = 256 threads; thread owns one 16-byte channel group and strides over rows; fp32 partials per thread (<= a few
+// thousand adds), block tree in shared memory, one fp64 atomic per channel per block.
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256) colstats_vec_kernel(const T* __restrict__ x, int ld, long long M, int C, double* __restrict__ sum,
+                                                           double* __restrict__ sumsq, int rows_per_block) {
+  constexpr int V = Vec<T>::N;
+  const int groups = C / V;                    // channel groups (<= 256 guaranteed by the launcher)
+  const int lanes = 256 / groups;              // row lanes
+  const int gidx = threadIdx.x % groups, lane = threadIdx.x / groups;
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  if (lane < lanes) {
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+      float v[V];
+      Vec<T>::load(x + r * ld + gidx * V, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s[i] += v[i];
+        if (SQ) q[i] = fmaf(v[i], v[i], q[i]);
+      }
+    }
+  }
+  __shared__ float sh[2][256][V + 1];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sh[0][threadIdx.x][i] = s[i];
+    if (SQ) sh[1][threadIdx.x][i] = q[i];
+  }
+  __syncthreads();
+  // thread t < C reduces channel t over the row lanes
+  for (int c = threadIdx.x; c < C; c += 256) {
+    int g = c / V, i = c % V;
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      a += sh[0][l * groups + g][i];
+      if (SQ) b += sh[1][l * groups + g][i];
+    }
+    atomicAdd(&sum[c], (double)a);
+    if (SQ) atomicAdd(&sumsq[c], (double)b);
+  }
+}
+template <typename T, bool SQ>
+__global__ void __launch_bounds__(256) colstats_scalar_kernel(const T* __restrict__ x, int ld, long long M, int C, double* __restrict__ sum,
+                                                              double* __restrict__ sumsq, int rows_per_block) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < C; c += 256) {   // uncoalesced but correct for any C / alignment
+    float a = 0.f, b = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      float v = to_f32(x[r * ld + c]);
+      a += v;
+      if (SQ) b = fmaf(v, v, b);
+    }
+    atomicAdd(&sum[c], (double)a);
+    if (SQ) atomicAdd(&sumsq[c], (double)b);
+  }
+}
+
+template <typename T>
+int colstats_launch(const T* x, int ld, long long M, int C, double* sum, double* sumsq, cudaStream_t s) {
+  if (M <= 0 || C <= 0) return 0;
+  int rows_per_block = 2048;
+  long long blocks = (M + rows_per_block - 1) / rows_per_block;
+  bool vec = vec_ok<T>(x, ld, C) && (C / Vec<T>::N <= 256) && (256 % (C / Vec<T>::N) == 0);
+  if (vec) {
+    if (sumsq) colstats_vec_kernel<T, true><<<(unsigned)blocks, 256, 0, s>>>(x, ld, M, C, sum, sumsq, rows_per_block);
+    else colstats_vec_kernel<T, false><<<(unsigned)blocks, 256, 0, s>>>(x, ld, M, C, sum, sumsq, rows_per_block);
+  } else {
+    if (sumsq) colstats_scalar_kernel<T, true><<<(unsigned)blocks, 256, 0, s>>>(x, ld, M, C, sum, sumsq, rows_per_block);
+    else colstats_scalar_kernel<T, false><<<(unsigned)blocks, 256, 0, s>>>(x, ld, M, C, sum, sumsq, rows_per_block);
+  }
+  return ich_check_launch("ich_colstats");
+}
+
+// ---- BatchNorm finalize ------------------------------------------------------------------------------------------
+// training: batch mean / biased var from the fp64 sums -> scale, shift, saved mean / invstd; running stats updated with
+// momentum and the UNBIASED variance (torch semantics).  The conv bias is not added by the conv kernel in training mode
+// (BatchNorm cancels it), so it is folded into the running-mean update here.
+// eval: scale/shift from the running stats, conv bias folded into the shift.
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd, int training) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  float cb = conv_bias ? conv_bias[c] : 0.f;
+  if (training) {
+    double mean = sum[c] / count;
+    double var = sumsq[c] / count - mean * mean;
+    if (var < 0) var = 0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = b - (float)mean * sc;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = invstd;
+    if (running_mean) {
+      double unbiased = count > 1 ? var * count / (count - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * ((float)mean + cb);
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  } else {
+    float invstd = 1.f / sqrtf(running_var[c] + eps);
+    float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = b + (cb - running_mean[c]) * sc;
+    save_mean[c] = running_mean[c] - cb;
+    save_invstd[c] = invstd;
+  }
+}
+
+// ---- z = [relu](y * scale[c] + shift[c]) --------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, T* __restrict__ z, int z_ld, long long M, int C,
+                                                         int relu) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V;
+  const long long total = M * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / groups;
+    int c = (int)(i - r * groups) * V;
+    float v[V];
+    if (VEC) Vec<T>::load(y + r * y_ld + c, v); else v[0] = to_f32(y[r * y_ld + c]);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float t = fmaf(v[k], scale[c + k], shift[c + k]);
+      v[k] = relu ? fmaxf(t, 0.f) : t;
+    }
+    if (VEC) Vec<T>::store(z + r * z_ld + c, v); else z[r * z_ld + c] = from_f32<T>(v[0]);
+  }
+}
+
+// ---- BatchNorm(+ReLU) backward ------------------------------------------------------------------------------------
+// pass 1: dbeta[c] = sum g, dgamma[c] = sum g * xhat, g = dz * [y*scale+shift > 0]
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd, long long M,
+                                                            int C, int relu, double* __restrict__ sums /*[2][C]*/, int rows_per_block) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V;
+  const int lanes = max(1, 256 / groups);
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  extern __shared__ float sh[];  // [2][C]
+  for (int c = threadIdx.x; c < 2 * C; c += 256) sh[c] = 0.f;
+  __syncthreads();
+  for (int gi = threadIdx.x % 256; gi < groups * lanes; gi += 256) {
+    const int g = gi % groups, lane = gi / groups, c = g * V;
+    float sb[V], sg[V], sc[V], sf[V], mu[V], is[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      sb[k] = sg[k] = 0.f;
+      sc[k] = scale[c + k]; sf[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k];
+    }
+    for (long long r = r0 + lane; r < r1; r += lanes) {
+      float a[V], b[V];
+      if (VEC) { Vec<T>::load(dz + r * dz_ld + c, a); Vec<T>::load(y + r * y_ld + c, b); }
+      else { a[0] = to_f32(dz[r * dz_ld + c]); b[0] = to_f32(y[r * y_ld + c]); }
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float gk = (!relu || fmaf(b[k], sc[k], sf[k]) > 0.f) ? a[k] : 0.f;
+        sb[k] += gk;
+        sg[k] = fmaf(gk, (b[k] - mu[k]) * is[k], sg[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      atomicAdd(&sh[c + k], sb[k]);
+      atomicAdd(&sh[C + c + k], sg[k]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) atomicAdd(&sums[c], (double)sh[c]);
+}
+
+// pass 2: dy = scale * (g - dbeta/M - xhat * dgamma/M)   (training) ;  dy = scale * g  (eval)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const double* __restrict__ sums, T* __restrict__ dy, int dy_ld, long long M, int C,
+                                                           int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V;
+  const long long total = M * groups;
+  const float invM = training ? (float)(1.0 / (double)M) : 0.f;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)sums[c];
+      if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / groups;
+    int c = (int)(i - r * groups) * V;
+    float a[V], b[V], o[V];
+    if (VEC) { Vec<T>::load(dz + r * dz_ld + c, a); Vec<T>::load(y + r * y_ld + c, b); }
+    else { a[0] = to_f32(dz[r * dz_ld + c]); b[0] = to_f32(y[r * y_ld + c]); }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float sc = scale[c + k];
+      float gk = (!relu || fmaf(b[k], sc, shift[c + k]) > 0.f) ? a[k] : 0.f;
+      float xhat = (b[k] - mean[c + k]) * invstd[c + k];
+      o[k] = sc * (gk - (float)sums[c + k] * invM - xhat * (float)sums[C + c + k] * invM);
+    }
+    if (VEC) Vec<T>::store(dy + r * dy_ld + c, o); else dy[r * dy_ld + c] = from_f32<T>(o[0]);
+  }
+}
+
+// ---- 2x max-pool (kernel 2 stride 2; depth factor FD = 2 or 1) ------------------------------------------------------
+// Tie rule = ATen max_pool3d_with_indices: scan (d,h,w) in order, update on strict '>' (NaN propagates) -> first max wins.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int N, int D,
+                                                          int H, int W, int C, int FD) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V, Do = D / FD, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Do * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long o = i / groups;
+    int c = (int)(i - o * groups) * V;
+    int wo = (int)(o % Wo); long long t = o / Wo;
+    int ho = (int)(t % Ho); t /= Ho;
+    int dd = (int)(t % Do); int n = (int)(t / Do);
+    float best[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) best[k] = -INFINITY;
+    for (int a = 0; a < FD; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int e = 0; e < 2; ++e) {
+          long long row = (((long long)n * D + dd * FD + a) * H + 2 * ho + b) * W + 2 * wo + e;
+          float v[V];
+          if (VEC) Vec<T>::load(x + row * x_ld + c, v); else v[0] = to_f32(x[row * x_ld + c]);
+#pragma unroll
+          for (int k = 0; k < V; ++k) if (v[k] > best[k] || v[k] != v[k]) best[k] = v[k];
+        }
+    if (VEC) Vec<T>::store(y + o * y_ld + c, best); else y[o * y_ld + c] = from_f32<T>(best[0]);
+  }
+}
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ x, int x_ld, const T* __restrict__ dy, int dy_ld,
+                                                          T* __restrict__ dx, int dx_ld, int N, int D, int H, int W, int C, int FD) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V, Do = D / FD, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Do * Ho * Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long o = i / groups;
+    int c = (int)(i - o * groups) * V;
+    int wo = (int)(o % Wo); long long t = o / Wo;
+    int ho = (int)(t % Ho); t /= Ho;
+    int dd = (int)(t % Do); int n = (int)(t / Do);
+    float best[V], g[V];
+    int arg[V];
+    if (VEC) Vec<T>::load(dy + o * dy_ld + c, g); else g[0] = to_f32(dy[o * dy_ld + c]);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+    for (int a = 0; a < FD; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int e = 0; e < 2; ++e) {
+          long long row = (((long long)n * D + dd * FD + a) * H + 2 * ho + b) * W + 2 * wo + e;
+          float v[V];
+          if (VEC) Vec<T>::load(x + row * x_ld + c, v); else v[0] = to_f32(x[row * x_ld + c]);
+#pragma unroll
+          for (int k = 0; k < V; ++k) if (v[k] > best[k] || v[k] != v[k]) { best[k] = v[k]; arg[k] = (a << 2) | (b << 1) | e; }
+        }
+    for (int a = 0; a < FD; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int e = 0; e < 2; ++e) {
+          long long row = (((long long)n * D + dd * FD + a) * H + 2 * ho + b) * W + 2 * wo + e;
+          float v[V];
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[k] = (arg[k] == ((a << 2) | (b << 1) | e)) ? g[k] : 0.f;
+          if (VEC) Vec<T>::store(dx + row * dx_ld + c, v); else dx[row * dx_ld + c] = from_f32<T>(v[0]);
+        }
+  }
+}
+
+// ---- channel-slab copy: dst[r][0:C] = src[r][0:C] with independent pitches (skip-connection concat / split) --------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) slab_copy_kernel(const T* __restrict__ src, int s_ld, T* __restrict__ dst, int d_ld, long long M, int C) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V;
+  const long long total = M * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / groups;
+    int c = (int)(i - r * groups) * V;
+    if (VEC) *reinterpret_cast<uint4*>(dst + r * d_ld + c) = *reinterpret_cast<const uint4*>(src + r * s_ld + c);
+    else dst[r * d_ld + c] = src[r * s_ld + c];
+  }
+}
+
+// ---- global average pool over the voxels of each sample: x [N][S][C] -> out fp32 [N][C]; and its backward -----------
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ x, int ld, float* __restrict__ out, long long S, int C) {
+  __shared__ float sh[8][33];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);   // gridDim.x == ceil(C / 32)
+  float a = 0.f;
+  if (c < C)
+    for (long long s = threadIdx.x >> 5; s < S; s += 8) a += to_f32(x[((long long)n * S + s) * ld + c]);
+  sh[threadIdx.x >> 5][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (threadIdx.x < 32 && c < C) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+    out[(long long)n * C + c] = t / (float)S;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dout, T* __restrict__ dx, int ld, long long S, int C, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long r = i / C;
+    long long n = r / S;
+    dx[r * ld + c] = from_f32<T>(dout[n * C + c] / (float)S);
+  }
+}
+
+}  // namespace
+
+#define DISPATCH_T(dtype, what, ...)                                   \
+  if (dtype == ICH_F32) { typedef float T; __VA_ARGS__ }               \
+  else if (dtype == ICH_BF16) { typedef bf16 T; __VA_ARGS__ }          \
+  else { ich_set_error("%s: bad dtype %d", what, dtype); return 1; }
+
+extern "C" {
+
+int ich_layout_nc_to_nl(const float* src, void* dst, int dtype, int N, int C, long long S, int dst_ld, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((long long)N * C * S == 0) return 0;
+  DISPATCH_T(dtype, "ich_layout_nc_to_nl", {
+    if (C == 1 && dst_ld == 1) {
+      cast_from_f32_kernel<T><<<grid_for((long long)N * S, 256), 256, 0, s>>>(src, (T*)dst, (long long)N * S);
+    } else {
+      dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, N), block(32, 8);
+      nc_to_nl_kernel<T><<<grid, block, 0, s>>>(src, (T*)dst, C, S, dst_ld);
+    }
+  })
+  return ich_check_launch("ich_layout_nc_to_nl");
+}
+
+int ich_layout_nl_to_nc(const void* src, int dtype, int src_ld, float* dst, int N, int C, long long S, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((long long)N * C * S == 0) return 0;
+  DISPATCH_T(dtype, "ich_layout_nl_to_nc", {
+    if (C == 1 && src_ld == 1) {
+      cast_to_f32_kernel<T><<<grid_for((long long)N * S, 256), 256, 0, s>>>((const T*)src, dst, (long long)N * S);
+    } else {
+      dim3 grid((unsigned)((S + 31) / 32), (C + 31) / 32, N), block(32, 8);
+      nl_to_nc_kernel<T><<<grid, block, 0, s>>>((const T*)src, dst, C, S, src_ld);
+    }
+  })
+  return ich_check_launch("ich_layout_nl_to_nc");
+}
+
+int ich_colstats(const void* x, int ld, int dtype, long long M, int C, double* sum, double* sumsq, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaMemsetAsync(sum, 0, sizeof(double) * C, s);
+  if (sumsq) cudaMemsetAsync(sumsq, 0, sizeof(double) * C, s);
+  DISPATCH_T(dtype, "ich_colstats", { return colstats_launch<T>((const T*)x, ld, M, C, sum, sumsq, s); })
+}
+
+int ich_bn_finalize(const double* sum, const double* sumsq, long long count, int C, const float* gamma, const float* beta,
+                    const float* conv_bias, float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                    float* shift, float* save_mean, float* save_invstd, int training, void* stream) {
+  ICH_REQUIRE(training || (running_mean && running_var), "ich_bn_finalize: eval mode needs running statistics");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, (double)count, C, gamma, beta, conv_bias, running_mean,
+                                                                        running_var, momentum, eps, scale, shift, save_mean, save_invstd,
+                                                                        training);
+  return ich_check_launch("ich_bn_finalize");
+}
+
+int ich_affine_act(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C,
+                   int relu, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M * C == 0) return 0;
+  DISPATCH_T(dtype, "ich_affine_act", {
+    if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C))
+      affine_act_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
+    else
+      affine_act_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
+  })
+  return ich_check_launch("ich_affine_act");
+}
+
+int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                   const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                   long long M, int C, int relu, int training, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M * C == 0) return 0;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
+  const int rows_per_block = 2048;
+  unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+  size_t shbytes = sizeof(float) * 2 * C;
+  DISPATCH_T(dtype, "ich_bn_act_bwd", {
+    bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
+    if (vec) {
+      bn_bwd_reduce_kernel<T, true><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block);
+      bn_bwd_apply_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta);
+    } else {
+      bn_bwd_reduce_kernel<T, false><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block);
+      bn_bwd_apply_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta);
+    }
+  })
+  return ich_check_launch("ich_bn_act_bwd");
+}
+
+int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE((FD == 1 || FD == 2) && D % FD == 0 && H % 2 == 0 && W % 2 == 0, "ich_maxpool2_fwd: grid %dx%dx%d not divisible by the pool", D, H, W);
+  long long outv = (long long)N * (D / FD) * (H / 2) * (W / 2);
+  if (outv * C == 0) return 0;
+  DISPATCH_T(dtype, "ich_maxpool2_fwd", {
+    if (vec_ok<T>(x, x_ld, C) && vec_ok<T>(y, y_ld, C))
+      maxpool_fwd_kernel<T, true><<<grid_for(outv * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, D, H, W, C, FD);
+    else
+      maxpool_fwd_kernel<T, false><<<grid_for(outv * C, 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, D, H, W, C, FD);
+  })
+  return ich_check_launch("ich_maxpool2_fwd");
+}
+
+int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W,
+                     int C, int FD, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE((FD == 1 || FD == 2) && D % FD == 0 && H % 2 == 0 && W % 2 == 0, "ich_maxpool2_bwd: grid %dx%dx%d not divisible by the pool", D, H, W);
+  long long outv = (long long)N * (D / FD) * (H / 2) * (W / 2);
+  if (outv * C == 0) return 0;
+  DISPATCH_T(dtype, "ich_maxpool2_bwd", {
+    if (vec_ok<T>(x, x_ld, C) && vec_ok<T>(dy, dy_ld, C) && vec_ok<T>(dx, dx_ld, C))
+      maxpool_bwd_kernel<T, true><<<grid_for(outv * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)x, x_ld, (const T*)dy, dy_ld, (T*)dx, dx_ld, N, D, H, W, C, FD);
+    else
+      maxpool_bwd_kernel<T, false><<<grid_for(outv * C, 256), 256, 0, s>>>((const T*)x, x_ld, (const T*)dy, dy_ld, (T*)dx, dx_ld, N, D, H, W, C, FD);
+  })
+  return ich_check_launch("ich_maxpool2_bwd");
+}
+
+int ich_slab_copy(const void* src, int src_ld, void* dst, int dst_ld, int dtype, long long M, int C, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (M * C == 0) return 0;
+  DISPATCH_T(dtype, "ich_slab_copy", {
+    if (vec_ok<T>(src, src_ld, C) && vec_ok<T>(dst, dst_ld, C))
+      slab_copy_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, dst_ld, M, C);
+    else
+      slab_copy_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, dst_ld, M, C);
+  })
+  return ich_check_launch("ich_slab_copy");
+}
+
+int ich_avgpool_fwd(const void* x, int ld, int dtype, float* out, int N, long long S, int C, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((long long)N * S * C == 0) return 0;
+  dim3 grid((C + 31) / 32, N);
+  DISPATCH_T(dtype, "ich_avgpool_fwd", { avgpool_fwd_kernel<T><<<grid, 256, 0, s>>>((const T*)x, ld, out, S, C); })
+  return ich_check_launch("ich_avgpool_fwd");
+}
+
+int ich_avgpool_bwd(const float* dout, void* dx, int ld, int dtype, int N, long long S, int C, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  long long total = (long long)N * S * C;
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, "ich_avgpool_bwd", { avgpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(dout, (T*)dx, ld, S, C, total); })
+  return ich_check_launch("ich_avgpool_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+"""Engine knobs. The reference's JSON configs and scripts stay unchanged, so knobs come from the environment
+ and can be overridden programmatically (tests, bench)."""
+import os
+import contextlib
+import torch
+
+_state = {
+    # 'bf16': bf16 activations + tcgen05 tensor-core convs (fp32 accumulate); 'fp32': fp32 activations, FFMA convs
+    'precision': os.environ.get('ICH_B200_PRECISION', 'bf16').lower(),
+    # compute d(loss)/d(input) when the caller set input.requires_grad_ (models/optim/UNet2D.py:137). The reference
+    # trainers never read it; default off saves the first layer's data-gradient.
+    'input_grad': os.environ.get('ICH_B200_INPUT_GRAD', '0') == '1',
+    # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
+    'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
+}
+
+
+def precision():
+    return _state['precision']
+
+
+def act_dtype():
+    return torch.bfloat16 if _state['precision'] == 'bf16' else torch.float32
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return 0
+    if dt == torch.bfloat16:
+        return 1
+    raise TypeError(f'ich_b200: unsupported activation dtype {dt}')
+
+
+def get(key):
+    return _state[key]
+
+
+def set(**kw):
+    for k, v in kw.items():
+        if k not in _state:
+            raise KeyError(k)
+        if k == 'precision' and v not in ('bf16', 'fp32'):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        _state[k] = v
+
+
+@contextlib.contextmanager
+def override(**kw):
+    old = dict(_state)
+    set(**kw)
+    try:
+        yield
+    finally:
+        _state.update(old)

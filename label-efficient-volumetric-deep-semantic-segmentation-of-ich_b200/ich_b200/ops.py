@@ -1,0 +1,556 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels. They own save-for-backward and workspaces (torch tensors);
+the library never allocates.  Internal activations are channel-last [N, D, H, W, C] tensors (2-D nets: D = 1) in the
+engine dtype (bf16 or fp32, ich_b200.config).  Call sites cite the reference lines they replace."""
+import torch
+from torch.autograd import Function
+
+from . import config
+from ._lib import call
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f'ich_b200.{what}: the hot path runs only on CUDA (sm_100a); there is no CPU fallback')
+
+
+def _rows(t):
+    """(ptr, channel pitch) of channel-last rows [N, D, H, W, C] (or [M, C]); the tensor may be a channel slab
+    (last-dim slice) of a wider contiguous buffer."""
+    if t.dim() == 2:
+        return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+    n, d, h, w, c = t.shape
+    st = t.stride()
+    if c > 1 and st[4] != 1:
+        raise RuntimeError('ich_b200: activation is not channel-last')
+    ld, mult = None, 1
+    for size, stride in ((w, st[3]), (h, st[2]), (d, st[1]), (n, st[0])):
+        if size > 1:
+            if ld is None:
+                if stride % mult:
+                    raise RuntimeError(f'ich_b200: irregular activation strides {st} for shape {tuple(t.shape)}')
+                ld = stride // mult
+            elif stride != ld * mult:
+                raise RuntimeError(f'ich_b200: irregular activation strides {st} for shape {tuple(t.shape)}')
+        mult *= size
+    return t.data_ptr(), (c if ld is None else ld)
+
+
+def _dt(t):
+    return config.dtype_code(t.dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# weight packs (derived caches, never serialised; invalidated when the optimizer mutates the parameter in place)
+# ---------------------------------------------------------------------------------------------------------------
+def _as5d(w):
+    return w if w.dim() == 5 else w.unsqueeze(2)
+
+
+def _pack(param, kind):
+    key = (param._version, param.data_ptr(), param.device)
+    cache = getattr(param, '_ich_packs', None)
+    if cache is None or cache[0] != key:
+        cache = (key, {})
+        param._ich_packs = cache
+    packs = cache[1]
+    if kind not in packs:
+        with torch.no_grad():
+            w = _as5d(param.detach())
+            if kind == 'conv_fwd':        # [taps*Cin][Cout] fp32
+                packs[kind] = w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).float().contiguous()
+            elif kind == 'conv_dgrad':    # [taps'*Cout][Cin] fp32, taps flipped
+                packs[kind] = w.flip(2, 3, 4).permute(2, 3, 4, 0, 1).reshape(-1, w.shape[1]).float().contiguous()
+            elif kind == 'conv_fwd_tc':   # [taps][Cout][Cin] bf16
+                packs[kind] = w.permute(2, 3, 4, 0, 1).reshape(-1, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
+            elif kind == 'conv_dgrad_tc':  # [taps'][Cin][Cout] bf16
+                packs[kind] = w.flip(2, 3, 4).permute(2, 3, 4, 1, 0).reshape(-1, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
+            elif kind == 'convT_fwd':     # [Cin][taps*Cout] fp32
+                packs[kind] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).float().contiguous()
+            elif kind == 'convT_dgrad':   # [taps*Cout][Cin] fp32
+                packs[kind] = w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).float().contiguous()
+            else:
+                raise KeyError(kind)
+    return packs[kind]
+
+
+def _ksize(weight):
+    w = _as5d(weight)
+    return w.shape[2], w.shape[3], w.shape[4]
+
+
+def _use_tc(x, cin, cout, k):
+    if not (config.get('tensor_cores') and x.dtype == torch.bfloat16):
+        return False
+    from ._lib import lib
+    n, d, h, w, _ = x.shape
+    return bool(lib().ich_conv_tc_supported(n, d, h, w, cin, cout, *k))
+
+
+def conv_forward(x, weight, bias, relu=False):
+    """y = conv(x) (+ bias) on channel-last rows; picks the tcgen05 kernel when eligible, else the FFMA kernel."""
+    n, d, h, w, cin = x.shape
+    cout = weight.shape[0]
+    k = _ksize(weight)
+    y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=x.device)
+    xp, xld = _rows(x)
+    if _use_tc(x, cin, cout, k):
+        call('ich_conv_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd_tc')), _p(bias), y.data_ptr(), cout, n, d, h, w, cin, cout, *k,
+             int(relu), _stream())
+    else:
+        call('ich_conv_fwd', xp, xld, _p(_pack(weight, 'conv_fwd')), _p(bias), y.data_ptr(), cout, _dt(x), n, d, h, w, cin, cout, *k,
+             int(relu), _stream())
+    return y
+
+
+def conv_dgrad(dy, weight):
+    n, d, h, w, cout = dy.shape
+    cin = weight.shape[1]
+    k = _ksize(weight)
+    dx = torch.empty((n, d, h, w, cin), dtype=dy.dtype, device=dy.device)
+    yp, yld = _rows(dy)
+    if _use_tc(dy, cout, cin, k):
+        call('ich_conv_tc_fwd', yp, yld, _p(_pack(weight, 'conv_dgrad_tc')), None, dx.data_ptr(), cin, n, d, h, w, cout, cin, *k, 0, _stream())
+    else:
+        call('ich_conv_fwd', yp, yld, _p(_pack(weight, 'conv_dgrad')), None, dx.data_ptr(), cin, _dt(dy), n, d, h, w, cout, cin, *k, 0, _stream())
+    return dx
+
+
+def conv_wgrad(x, dy, weight):
+    n, d, h, w, cin = x.shape
+    cout = weight.shape[0]
+    k = _ksize(weight)
+    dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+    xp, xld = _rows(x)
+    yp, yld = _rows(dy)
+    from ._lib import lib
+    if config.get('tensor_cores') and x.dtype == torch.bfloat16 and lib().ich_conv_tc_wgrad_supported(n, d, h, w, cin, cout, *k):
+        call('ich_conv_tc_wgrad', xp, xld, yp, yld, dw.data_ptr(), n, d, h, w, cin, cout, *k, _stream())
+    else:
+        call('ich_conv_wgrad', xp, xld, yp, yld, _dt(x), dw.data_ptr(), n, d, h, w, cin, cout, *k, _stream())
+    return dw
+
+
+def col_sum(x):
+    """fp64 per-channel sum over all rows of a channel-last tensor."""
+    c = x.shape[-1]
+    s = torch.empty(c, dtype=torch.float64, device=x.device)
+    xp, xld = _rows(x)
+    call('ich_colstats', xp, xld, _dt(x), x.numel() // c, c, s.data_ptr(), None, _stream())
+    return s
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------------------------
+class ToChannelsLast(Function):
+    """NC(D)HW fp32 (what the trainers feed, models/optim/UNet2D.py:137) -> engine N(D)HWC."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x, 'ToChannelsLast')
+        x = x.contiguous().float()
+        ctx.was_4d = x.dim() == 4
+        if ctx.was_4d:
+            x = x.unsqueeze(2)
+        n, c, d, h, w = x.shape
+        out = torch.empty((n, d, h, w, c), dtype=config.act_dtype(), device=x.device)
+        call('ich_layout_nc_to_nl', x.data_ptr(), out.data_ptr(), _dt(out), n, c, d * h * w, c, _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None or not config.get('input_grad'):
+            return None
+        gx = FromChannelsLast.forward(None, g.contiguous())
+        return gx.squeeze(2) if ctx.was_4d else gx
+
+
+class FromChannelsLast(Function):
+    """engine N(D)HWC -> NC(D)HW fp32 contiguous (callers .view() the result)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, d, h, w, c = x.shape
+        out = torch.empty((n, c, d, h, w), dtype=torch.float32, device=x.device)
+        xp, xld = _rows(x)
+        call('ich_layout_nl_to_nc', xp, _dt(x), xld, out.data_ptr(), n, c, d * h * w, _stream())
+        if ctx is not None:
+            ctx.dt = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().float()
+        n, c, d, h, w = g.shape
+        out = torch.empty((n, d, h, w, c), dtype=ctx.dt, device=g.device)
+        call('ich_layout_nc_to_nl', g.data_ptr(), out.data_ptr(), config.dtype_code(ctx.dt), n, c, d * h * w, c, _stream())
+        return out
+
+
+def to_channels_last(x):
+    return ToChannelsLast.apply(x)
+
+
+def from_channels_last(x, was_4d=False):
+    out = FromChannelsLast.apply(x)
+    return out.squeeze(2) if was_4d else out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Conv -> BatchNorm -> ReLU  (one unit of ConvBlock.forward, models/networks/UNet.py:173-174)
+# ---------------------------------------------------------------------------------------------------------------
+class ConvBnRelu(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, relu):
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[0]
+        m = n * d * h * w
+        dev = x.device
+        # training: BatchNorm cancels the conv bias, so the kernel skips it and bn_finalize folds it into running_mean
+        y = conv_forward(x, weight, None)
+        stats = torch.empty((4, cout), dtype=torch.float32, device=dev)      # scale, shift, mean, invstd
+        sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
+        if training:
+            call('ich_colstats', y.data_ptr(), cout, _dt(y), m, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+        call('ich_bn_finalize', sums[0].data_ptr(), sums[1].data_ptr(), m, cout, _p(gamma), _p(beta), _p(bias), _p(running_mean),
+             _p(running_var), BN_MOMENTUM, BN_EPS, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+             int(training), _stream())
+        z = torch.empty_like(y)
+        call('ich_affine_act', y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), z.data_ptr(), cout, _dt(y), m, cout, int(relu),
+             _stream())
+        ctx.save_for_backward(x, weight, y, stats)
+        ctx.training, ctx.relu = training, relu
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, weight, y, stats = ctx.saved_tensors
+        n, d, h, w, cout = y.shape
+        m = n * d * h * w
+        dz = dz.contiguous()
+        dy = torch.empty_like(y)
+        sums = torch.empty((2, cout), dtype=torch.float64, device=y.device)
+        dgamma = torch.empty(cout, dtype=torch.float32, device=y.device)
+        dbeta = torch.empty(cout, dtype=torch.float32, device=y.device)
+        call('ich_bn_act_bwd', dz.data_ptr(), cout, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+             stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(), _dt(y), m, cout, int(ctx.relu),
+             int(ctx.training), _stream())
+        need = ctx.needs_input_grad
+        dx = conv_dgrad(dy, weight) if need[0] else None
+        dw = conv_wgrad(x, dy, weight) if need[1] else None
+        db = None
+        if need[2]:
+            # training: d(loss)/d(bias) is exactly 0 (BatchNorm removes the mean); eval: sum of dy
+            db = torch.zeros(cout, dtype=torch.float32, device=y.device) if ctx.training else col_sum(dy).float()
+        return dx, dw, db, (dgamma if need[3] else None), (dbeta if need[4] else None), None, None, None, None
+
+
+class ConvBias(Function):
+    """Plain conv + bias (+ReLU): the 1x1 ConvHead layers (models/networks/UNet.py:228,238-242)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        z = conv_forward(x, weight, bias, relu)
+        ctx.save_for_backward(x, weight, z)
+        ctx.relu = relu
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, weight, z = ctx.saved_tensors
+        cout = z.shape[-1]
+        m = z.numel() // cout
+        dev = z.device
+        dz = dz.contiguous()
+        need = ctx.needs_input_grad
+        if ctx.relu:
+            # dy = dz * [z > 0]; reuse the BN-backward kernel in eval form with scale = 1, shift = 0 (it also yields db)
+            stats = torch.zeros((4, cout), dtype=torch.float32, device=dev)
+            stats[0].fill_(1.0)
+            stats[3].fill_(1.0)
+            sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
+            dy = torch.empty_like(z)
+            db = torch.empty(cout, dtype=torch.float32, device=dev)
+            call('ich_bn_act_bwd', dz.data_ptr(), cout, z.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                 stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, None, db.data_ptr(), _dt(z), m, cout, 1, 0, _stream())
+        else:
+            dy = dz
+            db = col_sum(dy).float() if need[2] else None
+        dx = conv_dgrad(dy, weight) if need[0] else None
+        dw = conv_wgrad(x, dy, weight) if need[1] else None
+        return dx, dw, (db if need[2] else None), None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MaxPool 2x (models/networks/UNet.py:82,109)
+# ---------------------------------------------------------------------------------------------------------------
+class MaxPool2(Function):
+    @staticmethod
+    def forward(ctx, x, fd):
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, d // fd, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+        xp, xld = _rows(x)
+        call('ich_maxpool2_fwd', xp, xld, y.data_ptr(), c, _dt(x), n, d, h, w, c, fd, _stream())
+        ctx.save_for_backward(x)
+        ctx.fd = fd
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, d, h, w, c = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty((n, d, h, w, c), dtype=x.dtype, device=x.device)
+        xp, xld = _rows(x)
+        call('ich_maxpool2_bwd', xp, xld, dy.data_ptr(), c, dx.data_ptr(), c, _dt(x), n, d, h, w, c, ctx.fd, _stream())
+        return dx, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ConvTranspose k2 s2 + torch.cat([res, up], 1) (models/networks/UNet.py:117-119): the up-sampled tensor is written
+# straight into its channel slab of the concat buffer.
+# ---------------------------------------------------------------------------------------------------------------
+class UpConvCat(Function):
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, fd):
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[1]
+        cres = res.shape[-1]
+        ctot = cres + cout
+        out = torch.empty((n, d * fd, h * 2, w * 2, ctot), dtype=x.dtype, device=x.device)
+        if tuple(res.shape[:4]) != tuple(out.shape[:4]):
+            raise RuntimeError(f'ich_b200: skip tensor {tuple(res.shape)} does not match the up-sampled grid {tuple(out.shape)}')
+        m_out = out.numel() // ctot
+        rp, rld = _rows(res)
+        call('ich_slab_copy', rp, rld, out.data_ptr(), ctot, _dt(x), m_out, cres, _stream())
+        up = out[..., cres:]
+        xp, xld = _rows(x)
+        call('ich_convT2_fwd', xp, xld, _p(_pack(weight, 'convT_fwd')), _p(bias), up.data_ptr(), ctot, _dt(x), n, d, h, w, cin, cout, fd,
+             _stream())
+        ctx.save_for_backward(x, weight)
+        ctx.fd, ctx.cres = fd, cres
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight = ctx.saved_tensors
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[1]
+        cres, fd = ctx.cres, ctx.fd
+        dout = dout.contiguous()
+        ctot = dout.shape[-1]
+        m_out = dout.numel() // ctot
+        need = ctx.needs_input_grad
+        dres = None
+        if need[1]:
+            dres = torch.empty(dout.shape[:4] + (cres,), dtype=dout.dtype, device=dout.device)
+            call('ich_slab_copy', dout.data_ptr(), ctot, dres.data_ptr(), cres, _dt(dout), m_out, cres, _stream())
+        dup = dout[..., cres:]
+        dx = dw = db = None
+        if need[0]:
+            dx = torch.empty_like(x)
+            call('ich_convT2_dgrad', dup.data_ptr(), ctot, _p(_pack(weight, 'convT_dgrad')), dx.data_ptr(), cin, _dt(x), n, d, h, w, cin, cout,
+                 fd, _stream())
+        if need[2]:
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            xp, xld = _rows(x)
+            call('ich_convT2_wgrad', xp, xld, dup.data_ptr(), ctot, _dt(x), dw.data_ptr(), n, d, h, w, cin, cout, fd, _stream())
+        if need[3]:
+            s = torch.empty(cout, dtype=torch.float64, device=x.device)
+            call('ich_colstats', dup.data_ptr(), ctot, _dt(dout), m_out, cout, s.data_ptr(), None, _stream())
+            db = s.float()
+        return dx, dres, dw, db, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# final 1x1 conv + Sigmoid / Softmax / Identity (models/networks/UNet.py:84-91,122) -> fp32 NC(D)HW
+# ---------------------------------------------------------------------------------------------------------------
+class Head(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[0]
+        s = d * h * w
+        out = torch.empty((n, cout, d, h, w), dtype=torch.float32, device=x.device)
+        wf = weight.detach().reshape(cout, cin).float().contiguous()
+        xp, xld = _rows(x)
+        call('ich_head_fwd', xp, xld, _dt(x), wf.data_ptr(), _p(bias), out.data_ptr(), n, s, cin, cout, act, _stream())
+        ctx.save_for_backward(x, weight, out)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, out = ctx.saved_tensors
+        n, d, h, w, cin = x.shape
+        cout = weight.shape[0]
+        s = d * h * w
+        dout = dout.contiguous().float()
+        need = ctx.needs_input_grad
+        xp, xld = _rows(x)
+        if cout == 1:
+            wf = weight.detach().reshape(cin).float().contiguous()
+            dx = torch.empty_like(x) if need[0] else None
+            dw = torch.empty(cin, dtype=torch.float32, device=x.device)
+            db = torch.empty(1, dtype=torch.float32, device=x.device)
+            call('ich_head1_bwd', xp, xld, _dt(x), wf.data_ptr(), out.data_ptr(), dout.data_ptr(), _p(dx), cin, dw.data_ptr(), db.data_ptr(),
+                 n * s, cin, ctx.act, _stream())
+            return dx, dw.view(weight.shape), db, None
+        dl = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=x.device)
+        call('ich_head_dlogit', out.data_ptr(), dout.data_ptr(), dl.data_ptr(), _dt(x), n, s, cout, ctx.act, _stream())
+        dx = conv_dgrad(dl, weight) if need[0] else None
+        dw = conv_wgrad(x, dl, weight) if need[1] else None
+        db = col_sum(dl).float() if need[2] else None
+        return dx, dw, db, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# AdaptiveAvgPool(1) (models/networks/UNet.py:295,318) -> fp32 [N, C]
+# ---------------------------------------------------------------------------------------------------------------
+class GlobalAvgPool(Function):
+    @staticmethod
+    def forward(ctx, x):
+        n, d, h, w, c = x.shape
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        xp, xld = _rows(x)
+        call('ich_avgpool_fwd', xp, xld, _dt(x), out.data_ptr(), n, d * h * w, c, _stream())
+        ctx.shape, ctx.dt = tuple(x.shape), x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, d, h, w, c = ctx.shape
+        g = g.contiguous().float()
+        dx = torch.empty(ctx.shape, dtype=ctx.dt, device=g.device)
+        call('ich_avgpool_bwd', g.data_ptr(), dx.data_ptr(), c, config.dtype_code(ctx.dt), n, d * h * w, c, _stream())
+        return dx
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------------------------
+_RED = {'none': 0, 'mean': 1, 'sum': 2}
+
+
+class SegLoss(Function):
+    """BinaryDiceLoss / ComboLoss (models/optim/LossFunctions.py:39-63,143-166) in one reduction pass + one backward pass."""
+
+    @staticmethod
+    def forward(ctx, pred, mask, p, eps, alpha_empty, w_bce, w_dice, beta, reduction):
+        _require_cuda(pred, 'SegLoss')
+        pred_c = pred.contiguous().float()
+        mask_c = mask.detach().contiguous().float()
+        b = pred_c.shape[0]
+        s = pred_c.numel() // b
+        acc = torch.empty((b, 5), dtype=torch.float64, device=pred.device)
+        per = torch.empty(b, dtype=torch.float32, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        call('ich_seg_loss_fwd', pred_c.data_ptr(), mask_c.data_ptr(), b, s, float(p), float(eps), float(alpha_empty), float(w_bce),
+             float(w_dice), float(beta), _RED[reduction], acc.data_ptr(), per.data_ptr(), loss.data_ptr(), _stream())
+        ctx.save_for_backward(pred_c, mask_c, acc)
+        ctx.args = (float(p), float(eps), float(alpha_empty), float(w_bce), float(w_dice), float(beta), reduction)
+        return per if reduction == 'none' else loss
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, mask, acc = ctx.saved_tensors
+        p, eps, alpha_empty, w_bce, w_dice, beta, reduction = ctx.args
+        b = pred.shape[0]
+        s = pred.numel() // b
+        g = g.float()
+        if reduction == 'none':
+            gscale = g.contiguous()
+        else:
+            gscale = (g / b if reduction == 'mean' else g).expand(b).contiguous()
+        dpred = torch.empty_like(pred)
+        call('ich_seg_loss_bwd', pred.data_ptr(), mask.data_ptr(), acc.data_ptr(), gscale.data_ptr(), b, s, p, eps, alpha_empty, w_bce, w_dice,
+             beta, dpred.data_ptr(), _stream())
+        # the trainers also set mask.requires_grad_ (models/optim/UNet2D.py:138) but never read the result -> None
+        return dpred, None, None, None, None, None, None, None, None
+
+
+class InfoNCE(Function):
+    """mean_rows( logsumexp_{j != i} S_ij - S_{i, pos(i)} ), S = cos / tau, on P [B][2A][E] (closed form of
+    models/optim/LossFunctions.py:208-230 and :328-339)."""
+
+    @staticmethod
+    def forward(ctx, P, tau):
+        _require_cuda(P, 'InfoNCE')
+        P = P.contiguous().float()
+        b, r, e = P.shape
+        dev = P.device
+        Pn = torch.empty_like(P)
+        aux = torch.empty((3, b * r), dtype=torch.float32, device=dev)     # invn, lse, rowloss
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        call('ich_infonce_fwd', P.data_ptr(), b, r, e, float(tau), Pn.data_ptr(), aux[0].data_ptr(), aux[1].data_ptr(), aux[2].data_ptr(),
+             loss.data_ptr(), counter.data_ptr(), _stream())
+        ctx.save_for_backward(Pn, aux)
+        ctx.tau = float(tau)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        Pn, aux = ctx.saved_tensors
+        b, r, e = Pn.shape
+        g = g.contiguous().float()
+        dP = torch.empty_like(Pn)
+        call('ich_infonce_bwd', Pn.data_ptr(), aux[0].data_ptr(), aux[1].data_ptr(), b, r, e, ctx.tau, g.data_ptr(), dP.data_ptr(), _stream())
+        return dP, None
+
+
+class RegionGather(Function):
+    """f1, f2 [bs][H][W][C] + corners [bs][A][2] -> P [bs][2A][K*K*C] (models/optim/LossFunctions.py:321-328)."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, corners, K):
+        _require_cuda(f1, 'RegionGather')
+        f1 = f1.contiguous().float()
+        f2 = f2.contiguous().float()
+        bs, H, W, C = f1.shape
+        A = corners.shape[1]
+        P = torch.empty((bs, 2 * A, K * K * C), dtype=torch.float32, device=f1.device)
+        for view, f in enumerate((f1, f2)):
+            call('ich_region_gather', f.data_ptr(), corners.data_ptr(), P.data_ptr(), bs, H, W, C, A, K, view, _stream())
+        ctx.save_for_backward(corners)
+        ctx.geom = (bs, H, W, C, A, K)
+        return P
+
+    @staticmethod
+    def backward(ctx, dP):
+        (corners,) = ctx.saved_tensors
+        bs, H, W, C, A, K = ctx.geom
+        dP = dP.contiguous()
+        outs = []
+        for view in range(2):
+            df = torch.empty((bs, H, W, C), dtype=torch.float32, device=dP.device)
+            call('ich_region_scatter', dP.data_ptr(), corners.data_ptr(), df.data_ptr(), bs, H, W, C, A, K, view, _stream())
+            outs.append(df)
+        return outs[0], outs[1], None, None
+
+
+def confusion_matrix(pred, target, threshold=None):
+    """batch_binary_confusion_matrix (utils/tensor_utils.py:12-36), optionally fused with the >= threshold of UNet2D.py:220.
+    Returns (tn, fp, fn, tp), each [B] fp32."""
+    _require_cuda(pred, 'confusion_matrix')
+    assert pred.shape == target.shape, f'Shapes do not match! {pred.shape} =/= {target.shape}'
+    assert pred.ndim > 1, f'The tensor must have more that a single dimension. {pred.ndim} dimension passed.'
+    p = pred.contiguous().float()
+    t = target.contiguous().float()
+    b = p.shape[0]
+    out = torch.empty((b, 4), dtype=torch.float64, device=p.device)
+    call('ich_confusion', p.data_ptr(), t.data_ptr(), b, p.numel() // b, -1.0 if threshold is None else float(threshold), out.data_ptr(),
+         _stream())
+    o = out.float()
+    return o[:, 0], o[:, 1], o[:, 2], o[:, 3]

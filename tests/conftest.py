@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'label-efficient-volumetric-deep-semantic-segmentation-of-ich_b200')
+for p in (ROOT, PKG, os.path.join(PKG, 'code')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def golden():
+    import torch
+
+    def load(name):
+        return torch.load(os.path.join(GOLDEN, name), map_location='cpu')
+    return load

@@ -1,0 +1,95 @@
+"""CPU: the C-ABI library builds / loads and exports every symbol include/ich_b200.h declares; the drop-in modules keep
+the reference's API surface (constructor validation, attribute tree, state-dict keys) and refuse to run without CUDA."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from ich_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    path = _lib.build()
+    assert os.path.exists(path)
+    protos = _lib.parse_header()
+    assert len(protos) >= 30
+    l = ctypes.CDLL(path)
+    for name in protos:
+        assert hasattr(l, name), f'{name} declared in include/ich_b200.h but not exported'
+    assert _lib.lib().ich_abi_version() == 1
+    assert _lib.lib().ich_last_error() is not None
+
+
+def test_state_dict_keys_match_reference(golden):
+    from src.models.networks.UNet import UNet, UNet_Encoder, Partial_UNet
+    for name, cls in [('unet3d_combo.pt', UNet), ('unet2d_dice.pt', UNet), ('unet3d_softmax.pt', UNet),
+                      ('encoder_infonce.pt', UNet_Encoder), ('partial_local_infonce.pt', Partial_UNet)]:
+        fx = golden(name)
+        net = cls(**fx['kwargs'])
+        assert list(net.state_dict().keys()) == list(fx['state_dict'].keys()), name
+        for k, v in net.state_dict().items():
+            assert v.shape == fx['state_dict'][k].shape and v.dtype == fx['state_dict'][k].dtype, (name, k)
+        net.load_state_dict(fx['state_dict'])
+    net = UNet(depth=4, use_3D=True, top_filter=16, midchannels_factor=2, p_dropout=0.0)
+    assert len(net.state_dict()) == 106 and sum(p.numel() for p in net.parameters()) == 962481      # SURVEY 8c anchors
+    net = UNet(depth=4, use_3D=True, top_filter=32, midchannels_factor=2, p_dropout=0.0)
+    assert sum(p.numel() for p in net.parameters()) == 3845729
+
+
+def test_constructor_validation():
+    from src.models.networks.UNet import UNet, ConvBlock, UNet_Encoder, Partial_UNet
+    from src.models.optim import LossFunctions as LF
+    with pytest.raises(TypeError):
+        UNet(p_dropout='0.5')
+    with pytest.raises(AssertionError):
+        UNet(depth=4, p_dropout=[0.1, 0.2])
+    with pytest.raises(AssertionError):
+        ConvBlock(1, 8, p_dropout=1.5)
+    with pytest.raises(AssertionError):
+        LF.BinaryDiceLoss(reduction='avg')
+    with pytest.raises(AssertionError):
+        LF.ComboLoss(alpha=1.5)
+    with pytest.raises(AssertionError):
+        LF.InfoNCELoss()
+    for n in ['BinaryDiceLoss', 'TverskyLoss', 'ComboLoss', 'InfoNCELoss', 'LocalInfoNCELoss', 'DiscountedL1', 'GDL', 'HSCLoss']:
+        assert hasattr(LF, n)
+    net = UNet(depth=3, top_filter=8, p_dropout=[0.0, 0.1, 0.2])
+    assert net.return_bottleneck is False and net.down_block[1].dropout.p == 0.1 and net.bottleneck_block.dropout.p == 0.2
+    assert isinstance(UNet(out_channels=3, depth=2, top_filter=4).final_activation, torch.nn.Softmax)
+    assert isinstance(UNet(use_final_activation=False, depth=2, top_filter=4).final_activation, torch.nn.Identity)
+    enc = UNet_Encoder(depth=3, top_filter=8, MLP_head=[16, 4])
+    assert enc.mlp_head.fc_layers[0].in_features == 32
+    pu = Partial_UNet(depth=4, n_decoder=2, top_filter=8, head_channel=[16, 4])
+    assert len(pu.up_samp) == 2 and pu.final_conv.conv_layers[0].in_channels == 16
+
+
+def test_losses_masks_and_sampling_match_reference_semantics():
+    import numpy as np
+    from src.models.optim import LossFunctions as LF
+    from oracle import losses_oracle as LO
+    l = LF.InfoNCELoss(set_size=3, tau=0.1, device='cpu')
+    eye = torch.diag(torch.ones(6)) + torch.diag(torch.ones(3), 3) + torch.diag(torch.ones(3), -3)
+    assert torch.equal(l.neg_mask, ~eye.bool())
+    loc = LF.LocalInfoNCELoss(tau=0.1, K=3, n_region=4, device='cpu')
+    np.random.seed(5)
+    a = loc.sample_region_corners((2, 12, 15, 8))
+    np.random.seed(5)
+    b = LO.sample_regions((2, 12, 15, 8), 3, 4)
+    assert (a == b).all() and a.shape == (2, 4, 2)
+    np.random.seed(5)
+    m = loc.get_sample_region_mask((2, 12, 15, 8))
+    assert m.shape == (2, 12, 15) and sorted(m.unique().tolist()) == [0, 1, 2, 3, 4] and (m > 0).sum().item() == 2 * 4 * 9
+
+
+def test_no_cpu_fallback(golden):
+    from src.models.networks.UNet import UNet
+    from src.models.optim.LossFunctions import ComboLoss, InfoNCELoss
+    fx = golden('unet3d_combo.pt')
+    net = UNet(**fx['kwargs'])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        net(fx['x'])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        ComboLoss()(torch.rand(1, 1, 4, 4), torch.rand(1, 1, 4, 4))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        InfoNCELoss(set_size=2, device='cpu')(torch.rand(2, 4), torch.rand(2, 4))

@@ -1,0 +1,355 @@
+"""GPU parity tests: every op of the hot path, called through the C-ABI (ich_b200.ops -> libich_b200.so), against the
+CPU oracle on identical inputs; then the drop-in modules end to end against the golden vectors generated from the
+unmodified reference.  Tolerances: fp32 mode 1e-4 relative, bf16 mode 1e-2 relative (north star), stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from ich_b200 import config, ops  # noqa: E402
+from oracle import unet_oracle as UO, losses_oracle as LO  # noqa: E402
+
+DEV = 'cuda'
+TOL = {'fp32': 1e-4, 'bf16': 1e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def cl(x, dtype):          # NCDHW cpu -> channel-last cuda
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(DEV, dtype)
+
+
+def nc(x):                 # channel-last cuda -> NCDHW cpu fp32
+    return x.float().permute(0, 4, 1, 2, 3).contiguous().cpu()
+
+
+CONV_CASES = [  # N, D, H, W, Cin, Cout, k3d
+    (2, 4, 8, 8, 1, 8, True), (1, 3, 5, 7, 3, 5, True), (2, 4, 8, 16, 16, 32, True), (1, 2, 4, 4, 64, 32, True),
+    (2, 1, 16, 16, 8, 16, False), (1, 1, 9, 11, 4, 6, False), (1, 8, 16, 16, 32, 32, True),
+]
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(case, prec):
+    n, d, h, w, cin, cout, k3d = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3 if k3d else 1, 3, 3, generator=g) * 0.2
+    b = torch.randn(cout, generator=g)
+    dy = torch.randn(n, cout, d, h, w, generator=g)
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+        if prec == 'bf16':   # identical (bf16-representable) operands on both sides; accumulation is fp32 in both
+            x, wt, dy = x.bfloat16().float(), wt.bfloat16().float(), dy.bfloat16().float()
+        xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+        yr = F.conv3d(xr, wr, b, padding=(1 if k3d else 0, 1, 1))
+        yr.backward(dy)
+        wg = wt.to(DEV).requires_grad_(True)
+        y = ops.conv_forward(cl(x, dt), wg, b.to(DEV))
+        dx = ops.conv_dgrad(cl(dy, dt), wg)
+        dw = ops.conv_wgrad(cl(x, dt), cl(dy, dt), wg)
+    tol = TOL[prec]
+    assert rel(nc(y), yr) < tol
+    assert rel(nc(dx), xr.grad) < tol
+    assert rel(dw, wr.grad) < (tol if prec == 'fp32' else 2e-3)    # fp32 output, exact-operand products
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('training', [True, False])
+def test_conv_bn_relu_unit(prec, training):
+    g = torch.Generator().manual_seed(3)
+    n, cin, cout, d, h, w = 2, 8, 16, 4, 8, 8
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    conv = torch.nn.Conv3d(cin, cout, 3, padding=1)
+    bn = torch.nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0, 0.3, generator=g)
+        bn.running_mean.normal_(0, 0.2, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+    dz = torch.randn(n, cout, d, h, w, generator=g)
+    if prec == 'bf16':
+        x, dz = x.bfloat16().float(), dz.bfloat16().float()
+        with torch.no_grad():
+            conv.weight.copy_(conv.weight.bfloat16().float())
+    import copy
+    conv_c, bn_c = copy.deepcopy(conv).to(DEV), copy.deepcopy(bn).to(DEV)
+    conv.train(training); bn.train(training)
+    xr = x.clone().requires_grad_(True)
+    zr = F.relu(bn(conv(xr)))
+    zr.backward(dz)
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+        xc = cl(x, dt).requires_grad_(True)
+        z = ops.ConvBnRelu.apply(xc, conv_c.weight, conv_c.bias, bn_c.weight, bn_c.bias, bn_c.running_mean, bn_c.running_var, training, True)
+        z.backward(cl(dz, dt))
+    tol = TOL[prec]
+    assert rel(nc(z), zr) < tol
+    # bf16: y is stored rounded to bf16 before normalisation -> gradients inherit ~2^-9 relative noise per element
+    gt = tol if prec == 'fp32' else 3e-2
+    assert rel(nc(xc.grad), xr.grad) < gt
+    assert rel(conv_c.weight.grad, conv.weight.grad) < gt
+    assert rel(bn_c.weight.grad, bn.weight.grad) < gt and rel(bn_c.bias.grad, bn.bias.grad) < gt
+    if training:
+        assert conv_c.bias.grad.abs().max().item() == 0.0          # exact zero; the reference's is fp noise
+        assert rel(bn_c.running_mean, bn.running_mean) < tol and rel(bn_c.running_var, bn.running_var) < tol
+    else:
+        assert rel(conv_c.bias.grad, conv.bias.grad) < gt
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('fd', [2, 1])
+def test_maxpool_with_ties(prec, fd):
+    g = torch.Generator().manual_seed(4)
+    n, c, d, h, w = 2, 16, 4 if fd == 2 else 1, 8, 8
+    x = torch.randint(0, 3, (n, c, d, h, w), generator=g).float()      # many exact ties, incl. zeros
+    dy = torch.randn(n, c, d // fd, h // 2, w // 2, generator=g).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool3d(xr, (fd, 2, 2), (fd, 2, 2))
+    yr.backward(dy)
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+        xc = cl(x, dt).requires_grad_(True)
+        y = ops.MaxPool2.apply(xc, fd)
+        y.backward(cl(dy, dt))
+    assert torch.equal(nc(y), yr)
+    assert torch.equal(nc(xc.grad), xr.grad)                          # tie rule = first max in (d, h, w) scan order
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('fd', [2, 1])
+def test_upconv_cat(prec, fd):
+    g = torch.Generator().manual_seed(5)
+    n, cin, cout, d, h, w = 2, 16, 8, 2 if fd == 2 else 1, 4, 4
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    res = torch.randn(n, cout, d * fd, h * 2, w * 2, generator=g)
+    wt = torch.randn(cin, cout, fd, 2, 2, generator=g) * 0.3
+    b = torch.randn(cout, generator=g)
+    dout = torch.randn(n, 2 * cout, d * fd, h * 2, w * 2, generator=g)
+    if prec == 'bf16':
+        x, res, wt, dout = [t.bfloat16().float() for t in (x, res, wt, dout)]
+    xr, rr, wr, br = [t.clone().requires_grad_(True) for t in (x, res, wt, b)]
+    outr = torch.cat([rr, F.conv_transpose3d(xr, wr, br, stride=(fd, 2, 2))], dim=1)
+    outr.backward(dout)
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+        xc, rc = cl(x, dt).requires_grad_(True), cl(res, dt).requires_grad_(True)
+        wc, bc = wt.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        out = ops.UpConvCat.apply(xc, rc, wc, bc, fd)
+        out.backward(cl(dout, dt))
+    tol = TOL[prec]
+    assert rel(nc(out), outr) < tol
+    assert rel(nc(xc.grad), xr.grad) < tol and rel(nc(rc.grad), rr.grad) < 1e-6
+    assert rel(wc.grad, wr.grad) < tol and rel(bc.grad, br.grad) < tol
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('cout,act', [(1, 1), (1, 0), (3, 2), (2, 0)])
+def test_head(prec, cout, act):
+    g = torch.Generator().manual_seed(6)
+    n, cin, d, h, w = 2, 32, 2, 4, 4
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    wt = torch.randn(cout, cin, 1, 1, 1, generator=g) * 0.3
+    b = torch.randn(cout, generator=g)
+    dout = torch.randn(n, cout, d, h, w, generator=g)
+    if prec == 'bf16':
+        x = x.bfloat16().float()
+    xr, wr, br = [t.clone().requires_grad_(True) for t in (x, wt, b)]
+    o = F.conv3d(xr, wr, br)
+    o = torch.sigmoid(o) if act == 1 else torch.softmax(o, 1) if act == 2 else o
+    o.backward(dout)
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+        xc = cl(x, dt).requires_grad_(True)
+        wc, bc = wt.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+        out = ops.Head.apply(xc, wc, bc, act)
+        out.backward(dout.to(DEV))
+    tol = TOL[prec]
+    assert out.shape == o.shape and out.is_contiguous() and out.dtype == torch.float32
+    assert rel(out, o) < 1e-5
+    assert rel(nc(xc.grad), xr.grad) < tol and rel(wc.grad, wr.grad) < tol and rel(bc.grad, br.grad) < tol
+
+
+def test_layout_roundtrip_and_avgpool():
+    g = torch.Generator().manual_seed(7)
+    for shape in [(2, 1, 4, 8, 8), (1, 5, 3, 5, 7), (2, 40, 2, 4, 4), (3, 7, 9, 11)]:
+        x = torch.randn(*shape, generator=g)
+        with config.override(precision='fp32', input_grad=True):
+            xc = x.to(DEV).requires_grad_(True)
+            c = ops.to_channels_last(xc)
+            back = ops.from_channels_last(c, was_4d=len(shape) == 4)
+            assert torch.equal(back.cpu(), x)
+            x5 = x if len(shape) == 5 else x.unsqueeze(2)
+            assert torch.equal(c.cpu(), x5.permute(0, 2, 3, 4, 1))
+            p = ops.GlobalAvgPool.apply(c)
+            assert rel(p, x5.mean(dim=(2, 3, 4))) < 1e-6
+            (p.sum() + back.sum()).backward()
+            assert rel(xc.grad, torch.full_like(x, 1.0 + 1.0 / x5[0, 0].numel())) < 1e-6
+
+
+def test_seg_losses_against_reference_vectors(golden):
+    from src.models.optim import LossFunctions as LF
+    fx = golden('losses.pt')
+    for c in fx['cases']:
+        cls = LF.BinaryDiceLoss if c['kind'] == 'dice' else LF.ComboLoss
+        p = fx['pred'].to(DEV).requires_grad_(True)
+        m = fx['mask'].to(DEV).requires_grad_(True)           # the trainers set requires_grad on the mask too
+        v = cls(**c['kwargs'])(p, m)
+        assert v.shape == c['value'].shape
+        assert rel(v, c['value']) < 1e-5, c['kwargs']
+        v.sum().backward()
+        assert rel(p.grad, c['grad']) < 1e-4, c['kwargs']
+
+
+def test_infonce_against_reference_vectors(golden):
+    from src.models.optim import LossFunctions as LF
+    fx = golden('losses.pt')
+    for c in fx['infonce']:
+        z1, z2 = c['z1'].to(DEV).requires_grad_(True), c['z2'].to(DEV).requires_grad_(True)
+        v = LF.InfoNCELoss(set_size=z1.shape[0], tau=c['tau'], device=DEV)(z1, z2)
+        assert abs(v.item() - c['value'].item()) < 1e-4 * abs(c['value'].item())
+        v.backward()
+        assert rel(z1.grad, c['g1']) < 1e-4 and rel(z2.grad, c['g2']) < 1e-4
+    for c in fx['local']:
+        f1, f2 = c['f1'].to(DEV).requires_grad_(True), c['f2'].to(DEV).requires_grad_(True)
+        np.random.seed(c['np_seed'])
+        v = LF.LocalInfoNCELoss(tau=c['tau'], K=c['K'], n_region=c['n_region'], device=DEV)(f1, f2)
+        assert abs(v.item() - c['value'].item()) < 1e-4 * abs(c['value'].item())
+        v.backward()
+        assert rel(f1.grad, c['g1']) < 1e-4 and rel(f2.grad, c['g2']) < 1e-4
+
+
+def test_confusion_matrix():
+    from src.utils.tensor_utils import batch_binary_confusion_matrix
+    g = torch.Generator().manual_seed(8)
+    p = (torch.rand(3, 1, 4, 8, 8, generator=g) > 0.5).float()
+    t = (torch.rand(3, 1, 4, 8, 8, generator=g) > 0.7).float()
+    got = batch_binary_confusion_matrix(p.to(DEV), t.to(DEV))
+    want = LO.batch_binary_confusion(p, t)
+    for a, b in zip(got, want):
+        assert torch.equal(a.cpu(), b)                               # integer-valued counts: exact
+
+
+def _load(cls, fx):
+    net = cls(**fx['kwargs'])
+    net.load_state_dict(fx['state_dict'])
+    return net.to(DEV).train()
+
+
+def _grad_check(net, fx, tol, bias_abs):
+    worst = 0.0
+    for k, p in net.named_parameters():
+        ref = fx['grads'][k]
+        if ('.conv1.bias' in k or '.conv2.bias' in k) and 'final' not in k:
+            assert p.grad.abs().max().item() <= bias_abs, k       # dead pre-BN bias: exact 0 here, fp noise in the reference
+            continue
+        worst = max(worst, rel(p.grad, ref))
+    assert worst < tol, worst
+
+
+def test_unet3d_end_to_end_fp32(golden):
+    """fp32 verification mode vs the reference golden run: outputs / loss 1e-4, bit-exact masks, running stats, eval."""
+    from src.models.networks.UNet import UNet
+    from src.models.optim.LossFunctions import ComboLoss
+    fx = golden('unet3d_combo.pt')
+    with config.override(precision='fp32'):
+        net = _load(UNet, fx)
+        x = fx['x'].to(DEV).requires_grad_(True)
+        m = fx['mask'].to(DEV).requires_grad_(True)
+        out = net(x)
+        loss = ComboLoss(**fx['loss_kwargs'])(out, m)
+        loss.backward()
+        assert out.shape == fx['out_train'].shape and out.is_contiguous()
+        assert rel(out, fx['out_train']) < 1e-4
+        assert abs(loss.item() - fx['loss'].item()) < 1e-4 * abs(fx['loss'].item())
+        assert torch.equal((out >= 0.5).cpu(), fx['out_train'] >= 0.5)
+        _grad_check(net, fx, 5e-3, 0.0)          # deep weight-grads: the fp32 reference itself is only ~2e-3 vs fp64
+        sd = net.state_dict()
+        for k, v in fx['state_dict_after'].items():
+            if 'running' in k or 'num_batches' in k:
+                assert rel(sd[k], v) < 1e-4, k
+        net.load_state_dict(fx['state_dict_after'])
+        net.eval()
+        with torch.no_grad():
+            ev = net(fx['x'].to(DEV))
+        assert rel(ev, fx['out_eval']) < 1e-4
+        assert torch.equal((ev >= 0.5).cpu(), fx['out_eval'] >= 0.5)
+
+
+def test_unet3d_end_to_end_bf16(golden):
+    from src.models.networks.UNet import UNet
+    from src.models.optim.LossFunctions import ComboLoss
+    fx = golden('unet3d_combo.pt')
+    with config.override(precision='bf16'):
+        net = _load(UNet, fx)
+        out = net(fx['x'].to(DEV))
+        loss = ComboLoss(**fx['loss_kwargs'])(out, fx['mask'].to(DEV))
+        loss.backward()
+        assert rel(out, fx['out_train']) < 1e-2
+        assert abs(loss.item() - fx['loss'].item()) < 1e-2 * abs(fx['loss'].item())
+        dice = lambda p, t: (2 * (p * t).sum((1, 2, 3, 4)) + 1) / (p.sum((1, 2, 3, 4)) + t.sum((1, 2, 3, 4)) + 1)
+        mk = fx['mask']
+        assert (dice((out >= 0.5).float().cpu(), mk) - dice((fx['out_train'] >= 0.5).float(), mk)).abs().max() < 1e-3
+
+
+def test_unet2d_end_to_end_fp32(golden):
+    from src.models.networks.UNet import UNet
+    from src.models.optim.LossFunctions import BinaryDiceLoss
+    fx = golden('unet2d_dice.pt')
+    with config.override(precision='fp32'):
+        net = _load(UNet, fx)
+        out = net(fx['x'].to(DEV))
+        loss = BinaryDiceLoss(**fx['loss_kwargs'])(out, fx['mask'].to(DEV))
+        loss.backward()
+        assert out.shape == fx['out_train'].shape
+        assert rel(out, fx['out_train']) < 1e-4 and abs(loss.item() - fx['loss'].item()) < 1e-5
+        _grad_check(net, fx, 5e-3, 0.0)
+
+
+def test_softmax_head_and_bottleneck_fp32(golden):
+    from src.models.networks.UNet import UNet
+    fx = golden('unet3d_softmax.pt')
+    with config.override(precision='fp32'):
+        net = _load(UNet, fx)
+        net.return_bottleneck = True
+        out, xb = net(fx['x'].to(DEV))
+        assert rel(out, fx['out_train']) < 1e-4 and rel(xb, fx['bottleneck']) < 1e-4
+        assert xb.is_contiguous() and xb.view(xb.shape[0], -1).shape[0] == 1
+        assert torch.equal(out.argmax(1).cpu(), fx['out_train'].argmax(1))          # bit-exact argmax masks
+
+
+def test_encoder_infonce_end_to_end_fp32(golden):
+    from src.models.networks.UNet import UNet_Encoder
+    from src.models.optim.LossFunctions import InfoNCELoss
+    fx = golden('encoder_infonce.pt')
+    with config.override(precision='fp32'):
+        net = _load(UNet_Encoder, fx)
+        z1 = F.normalize(net(fx['x1'].to(DEV)), dim=1)
+        z2 = F.normalize(net(fx['x2'].to(DEV)), dim=1)
+        loss = InfoNCELoss(set_size=4, tau=fx['tau'], device=DEV)(z1, z2)
+        loss.backward()
+        assert rel(z1, fx['z1']) < 1e-4 and rel(z2, fx['z2']) < 1e-4
+        assert abs(loss.item() - fx['loss'].item()) < 1e-4 * abs(fx['loss'].item())
+        _grad_check(net, fx, 2e-2, 0.0)
+        net.return_bottleneck = True
+        _, pooled = net(fx['x1'].to(DEV))
+        assert pooled.shape == (4, 32, 1, 1, 1)
+
+
+def test_partial_unet_local_infonce_end_to_end_fp32(golden):
+    from src.models.networks.UNet import Partial_UNet
+    from src.models.optim.LossFunctions import LocalInfoNCELoss
+    fx = golden('partial_local_infonce.pt')
+    with config.override(precision='fp32'):
+        net = _load(Partial_UNet, fx)
+        f1, f2 = net(fx['x1'].to(DEV)), net(fx['x2'].to(DEV))
+        np.random.seed(fx['np_seed'])
+        loss = LocalInfoNCELoss(device=DEV, **fx['loss_kwargs'])(f1, f2)
+        loss.backward()
+        assert rel(f1, fx['f1']) < 1e-4 and rel(f2, fx['f2']) < 1e-4
+        assert abs(loss.item() - fx['loss'].item()) < 1e-4 * abs(fx['loss'].item())
+        _grad_check(net, fx, 2e-2, 0.0)
