@@ -112,7 +112,7 @@ class LocalInfoNCELoss(nn.Module):
         gh, gw = H // self.K, W // self.K
         idx_col = np.random.choice(gh * gw, self.n_region, replace=False)
         idx = np.random.rand(bs, gh * gw).argsort(axis=1)[:, idx_col]
-        return np.stack([(idx // gw) * self.K, (idx % gw) * self.K], axis=-1).astype(np.int32)
+        return np.ascontiguousarray(np.stack([(idx // gw) * self.K, (idx % gw) * self.K], axis=-1), dtype=np.int32)
 
     def get_sample_region_mask(self, feature_shape):
         """Region-label mask (B x H x W, labels 1..n_region) as the reference returns it; not used by forward."""

