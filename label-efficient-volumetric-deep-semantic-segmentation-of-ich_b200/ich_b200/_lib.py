@@ -100,8 +100,19 @@ def lib():
     return _lib
 
 
+# kernels launched per entry point (memsets not counted); everything else launches exactly one
+KERNELS_PER_CALL = {'ich_bn_act_bwd': 2, 'ich_seg_loss_fwd': 2, 'ich_infonce_fwd': 2}
+LAUNCHES = {}
+
+
+def launches():
+    """Total number of ich_b200 CUDA kernels launched by this process so far."""
+    return sum(LAUNCHES.values())
+
+
 def call(name, *args):
     l = lib()
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + KERNELS_PER_CALL.get(name, 1)
     rc = getattr(l, name)(*args)
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {l.ich_last_error().decode()}')

@@ -97,8 +97,38 @@ def _use_tc(x, cin, cout, k):
     return bool(lib().ich_conv_tc_supported(n, d, h, w, cin, cout, *k))
 
 
+# bench.py sets PROFILE = [] to collect (kind, flops, start_event, end_event) per conv kernel launch
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+        return False
+
+
 def conv_forward(x, weight, bias, relu=False):
     """y = conv(x) (+ bias) on channel-last rows; picks the tcgen05 kernel when eligible, else the FFMA kernel."""
+    n, d, h, w, cin = x.shape
+    cout = weight.shape[0]
+    k = _ksize(weight)
+    with _Timed('fwd', 2.0 * n * d * h * w * cin * cout * k[0] * k[1] * k[2]):
+        return _conv_forward(x, weight, bias, relu)
+
+
+def _conv_forward(x, weight, bias, relu):
     n, d, h, w, cin = x.shape
     cout = weight.shape[0]
     k = _ksize(weight)
@@ -117,6 +147,14 @@ def conv_dgrad(dy, weight):
     n, d, h, w, cout = dy.shape
     cin = weight.shape[1]
     k = _ksize(weight)
+    with _Timed('dgrad', 2.0 * n * d * h * w * cin * cout * k[0] * k[1] * k[2]):
+        return _conv_dgrad(dy, weight)
+
+
+def _conv_dgrad(dy, weight):
+    n, d, h, w, cout = dy.shape
+    cin = weight.shape[1]
+    k = _ksize(weight)
     dx = torch.empty((n, d, h, w, cin), dtype=dy.dtype, device=dy.device)
     yp, yld = _rows(dy)
     if _use_tc(dy, cout, cin, k):
@@ -127,6 +165,14 @@ def conv_dgrad(dy, weight):
 
 
 def conv_wgrad(x, dy, weight):
+    n, d, h, w, cin = x.shape
+    cout = weight.shape[0]
+    k = _ksize(weight)
+    with _Timed('wgrad', 2.0 * n * d * h * w * cin * cout * k[0] * k[1] * k[2]):
+        return _conv_wgrad(x, dy, weight)
+
+
+def _conv_wgrad(x, dy, weight):
     n, d, h, w, cin = x.shape
     cout = weight.shape[0]
     k = _ksize(weight)
