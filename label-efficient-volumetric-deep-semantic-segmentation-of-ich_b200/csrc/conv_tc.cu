@@ -1,14 +1,417 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution (placeholder until the kernel lands: reports "unsupported").
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a: 3x3x3 (or 1x3x3) "same" conv on channel-last bf16, fp32
+// accumulate in tensor memory.  Used for the forward pass and, with the flipped/transposed weight pack, the data gradient.
+// Replaces the cuDNN kernels behind nn.Conv3d/Conv2d at reference models/networks/UNet.py:153,155,158,160.
+//
+// Shift-GEMM on a zero-padded slab (no im2col, no per-tap reloads):
+//   * one TMA box load brings a slab of the input -- KD planes x (R+2) rows x (WB+2) positions x 16 channels -- into shared
+//     memory; out-of-bounds rows / columns are zero-filled by TMA, which IS the convolution padding.  The tensor map
+//     splits C into (8, C/8) so the slab lands as [plane][chan8-chunk][row][pos][8 ch]: the canonical NO-SWIZZLE K-major
+//     UMMA layout (8 rows x 16 B core matrices, 128 B apart) for ANY starting position.
+//   * a tap (kd,kh,kw) is therefore just a different descriptor start address: +kd*plane + (kh*PW + kw)*16 B.  Each M
+//     tile (128 consecutive flat positions of the padded slab) issues KD*9 MMAs of K=16 per channel chunk; positions that
+//     fall on the halo columns produce garbage accumulator rows that the epilogue discards.
+//   * weights [tap][Cout][Cin] arrive the same way ([tap][chunk][cout][8 ch]) as the B operand.
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue (tcgen05.ld -> bias/ReLU ->
+//     bf16 -> 16 B global stores).  Two smem stages, two TMEM accumulator sets; persistent CTAs, static round-robin.
 #include "common.cuh"
-extern "C" {
-int ich_conv_tc_supported(int, int, int, int, int, int, int, int, int) { return 0; }
-int ich_conv_tc_fwd(const void*, int, const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, void*) {
-  ich_set_error("ich_conv_tc_fwd: not built");
-  return 1;
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box -- trap after ~2 s.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// No-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// 8-row x 16-byte core matrices; LBO = byte distance between the two K halves (chunks of 8 channels),
+// SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+struct Params {
+  int N, D, H, W, Cin, Cout, KD;
+  int WB, PW, R, RB, T, row_mode, NB;
+  int n_wb, n_rb, n_nb, KC, taps;
+  int nacc;
+  uint32_t a_bytes, a_tx_bytes, b_bytes, stage_bytes, tmem_cols;
+  long long n_items;
+  bf16* y;
+  int y_ld;
+  const float* bias;
+  int relu;
+};
+
+constexpr int STAGES = 2;
+constexpr int NUM_THREADS = 192;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stage0 A|B][stage1 A|B] ... then barriers
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int planes_lo = (p.KD == 3) ? 1 : 0;     // slab plane 0 corresponds to d - planes_lo
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        long long t = item;
+        const int nb = (int)(t % p.n_nb); t /= p.n_nb;
+        const int wb = (int)(t % p.n_wb); t /= p.n_wb;
+        const int rb = (int)(t % p.n_rb); t /= p.n_rb;
+        const int d = (int)(t % p.D); const int n = (int)(t / p.D);
+        const int w0 = wb * p.WB, h0 = rb * p.R;
+        for (int kc = 0; kc < p.KC; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_bytes;
+          mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
+          tma_load_5d(sa, &map_x, &full_bar[stage], 0, w0 - 1, h0 - 1, kc * 2, n * p.D + d - planes_lo);
+          tma_load_4d(sb, &map_w, &full_bar[stage], 0, nb * p.NB, kc * 2, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)p.RB * p.PW * 16u;      // chunk (8-channel) stride inside a plane
+      const uint32_t a_plane = 2u * a_lbo;                     // plane stride (2 chunks per plane per stage)
+      const uint32_t b_lbo = (uint32_t)p.NB * 16u;
+      const uint32_t b_tap = 2u * b_lbo;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        long long t = item / p.n_nb / p.n_wb / p.n_rb;
+        const int d = (int)(t % p.D);
+        const int kd_lo = (p.KD == 3 && d == 0) ? 1 : 0;
+        const int kd_hi = (p.KD == 3) ? ((d == p.D - 1) ? 1 : 2) : 0;
+        const int acc = (p.nacc == 2) ? (it & 1) : 0;
+        const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.T * p.NB);
+        for (int kc = 0; kc < p.KC; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + p.a_bytes;
+          bool first = (kc == 0);
+          for (int kd = kd_lo; kd <= kd_hi; ++kd)
+            for (int kh = 0; kh < 3; ++kh)
+              for (int kw = 0; kw < 3; ++kw) {
+                const int tap = (kd * 3 + kh) * 3 + kw;
+                const uint64_t bdesc = umma_desc(sb + (uint32_t)tap * b_tap, b_lbo, 128u);
+                const uint32_t a_off = sa + (uint32_t)kd * a_plane + (uint32_t)(kh * p.PW + kw) * 16u;
+                for (int tt = 0; tt < p.T; ++tt) {
+                  const uint32_t base = p.row_mode ? (uint32_t)(tt * p.PW) : (uint32_t)(tt * 128);
+                  const uint64_t adesc = umma_desc(a_off + base * 16u, a_lbo, 128u);
+                  umma_bf16(d_tmem + (uint32_t)(tt * p.NB), adesc, bdesc, idesc, first ? 0u : 1u);
+                }
+                first = false;
+              }
+          umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                // accumulators complete
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (2..5): TMEM lane quadrant = warp % 4
+    const int q = warp & 3;
+    const int l = q * 32 + lane;
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      long long t = item;
+      const int nb = (int)(t % p.n_nb); t /= p.n_nb;
+      const int wb = (int)(t % p.n_wb); t /= p.n_wb;
+      const int rb = (int)(t % p.n_rb); t /= p.n_rb;
+      const int d = (int)(t % p.D); const int n = (int)(t / p.D);
+      const int w0 = wb * p.WB, h0 = rb * p.R, n0 = nb * p.NB;
+      const int acc = (p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      for (int tt = 0; tt < p.T; ++tt) {
+        const int f = (p.row_mode ? tt * p.PW : tt * 128) + l;
+        const int r = f / p.PW, pos = f - r * p.PW;
+        const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W);
+        const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
+        bf16* yrow = p.y + vox * p.y_ld + n0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
+        for (int c0 = 0; c0 < p.NB; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f32[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              float a = __uint_as_float(v[k]);
+              if (p.bias) a += p.bias[n0 + c0 + k];
+              if (p.relu) a = fmaxf(a, 0.f);
+              f32[k] = a;
+            }
+            Vec<bf16>::store(yrow + c0, f32);
+            Vec<bf16>::store(yrow + c0 + 8, f32 + 8);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  });
+  return fn;
+}
+
+struct Plan {
+  bool ok = false;
+  Params p{};
+  size_t smem_bytes = 0;
+};
+
+constexpr size_t SMEM_LIMIT = 227 * 1024 - 4096;   // dynamic limit: leave room for the static barriers / alignment
+
+Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
+  Plan pl;
+  if (KH != 3 || KW != 3 || (KD != 1 && KD != 3)) return pl;
+  if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
+  if (N <= 0 || D <= 0 || H <= 0 || W < 4) return pl;
+  int WB;
+  if (W <= 128) WB = W;
+  else if (W % 128 == 0) WB = 128;
+  else return pl;
+  const int PW = WB + 2;
+  int NB = 0;
+  for (int c = 64; c >= 16; c -= 16)
+    if (Cout % c == 0) { NB = c; break; }
+  if (!NB) return pl;
+  const int taps = KD * 9;
+  const uint32_t b_bytes = (uint32_t)taps * 2u * NB * 16u;
+  const bool row_mode = (WB == 128);
+  long long best_cost = -1;
+  int bestR = 0, bestT = 0, bestAcc = 0;
+  size_t best_smem = 0;
+  uint32_t best_a = 0;
+  for (int R = 1; R <= H && R <= 64; ++R) {
+    const int RB = R + 2;
+    const int T = row_mode ? R : (((R - 1) * PW + WB) + 127) / 128;
+    int nacc = 0;
+    if (2 * T * NB <= 512) nacc = 2;
+    else if (T * NB <= 512) nacc = 1;
+    else continue;
+    uint32_t a_bytes = (uint32_t)KD * 2u * RB * PW * 16u;
+    a_bytes = (a_bytes + 127u) & ~127u;
+    long long over = row_mode ? 0 : ((long long)(128 * T + 2 * PW + 2) - (long long)RB * PW) * 16;
+    if (over < 0) over = 0;
+    size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
+    size_t total = STAGES * stage + (size_t)over + 1024;   // +1024: manual alignment of the dynamic base
+    if (total > SMEM_LIMIT) continue;
+    long long blocks = (H + R - 1) / R;
+    long long cost = blocks * T * 1000 + blocks * RB * 20 + (nacc == 1 ? blocks * T * 150 : 0);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost; bestR = R; bestT = T; bestAcc = nacc; best_smem = total; best_a = a_bytes;
+    }
+  }
+  if (best_cost < 0) return pl;
+  Params& p = pl.p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD;
+  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2; p.T = bestT; p.row_mode = row_mode; p.NB = NB;
+  p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / 16; p.taps = taps;
+  p.nacc = bestAcc;
+  p.a_bytes = best_a;
+  p.a_tx_bytes = (uint32_t)KD * 2u * p.RB * PW * 16u;
+  p.b_bytes = b_bytes;
+  p.stage_bytes = (uint32_t)(((size_t)best_a + b_bytes + 1023) & ~(size_t)1023);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(bestAcc * bestT * NB)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.n_items = (long long)N * D * p.n_rb * p.n_wb * p.n_nb;
+  pl.smem_bytes = best_smem;
+  pl.ok = true;
+  return pl;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
+  if (!get_encode()) return 0;
+  return make_plan(N, D, H, W, Cin, Cout, KD, KH, KW).ok ? 1 : 0;
+}
+
+int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W, int Cin,
+                    int Cout, int KD, int KH, int KW, int relu, void* stream) {
+  Plan pl = make_plan(N, D, H, W, Cin, Cout, KD, KH, KW);
+  ICH_REQUIRE(pl.ok, "ich_conv_tc_fwd: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
+  ICH_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wpack_bf16 & 15) == 0,
+              "ich_conv_tc_fwd: pointers / pitches must be 16-byte aligned (x_ld %d, y_ld %d)", x_ld, y_ld);
+  EncodeTiledFn enc = get_encode();
+  ICH_REQUIRE(enc != nullptr, "ich_conv_tc_fwd: cuTensorMapEncodeTiled not available");
+  Params& p = pl.p;
+  p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
+
+  CUtensorMap map_x, map_w;
+  {
+    // x as (c8, W, H, C/8, N*D): the chunk dim makes the box land as [plane][chunk][row][pos][8ch]
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)N * D};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, 16, (cuuint64_t)H * W * x_ld * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.RB, 2, (cuuint32_t)KD};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_fwd: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+  }
+  {
+    // w [taps][Cout][Cin] as (c8, Cout, Cin/8, taps)
+    cuuint64_t dims[4] = {8, (cuuint64_t)Cout, (cuuint64_t)(Cin / 8), (cuuint64_t)p.taps};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[4] = {8, (cuuint32_t)p.NB, 2, (cuuint32_t)p.taps};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_fwd: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e != cudaSuccess) cudaGetLastError();
+    ICH_REQUIRE(e == cudaSuccess, "ich_conv_tc_fwd: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
+  size_t smem = pl.smem_bytes;
+  conv_tc_kernel<<<(unsigned)grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_x, map_w, p);
+  return ich_check_launch("ich_conv_tc_fwd");
+}
+
 int ich_conv_tc_wgrad_supported(int, int, int, int, int, int, int, int, int) { return 0; }
 int ich_conv_tc_wgrad(const void*, int, const void*, int, float*, int, int, int, int, int, int, int, int, int, void*) {
   ich_set_error("ich_conv_tc_wgrad: not built");
   return 1;
 }
-}
+
+}  // extern "C"

@@ -354,3 +354,48 @@ def test_partial_unet_local_infonce_end_to_end_fp32(golden):
         assert rel(f1, fx['f1']) < 1e-4 and rel(f2, fx['f2']) < 1e-4
         assert abs(loss.item() - fx['loss'].item()) < 1e-4 * abs(fx['loss'].item())
         _grad_check(net, fx, 2e-2, 0.0)
+
+
+TC_CASES = [  # N, D, H, W, Cin, Cout, k3d  -- shapes the tcgen05 kernel must take (asserted), covering row / flat tiling modes
+    (1, 2, 8, 128, 16, 32, True),       # row mode (W = 128), single channel chunk
+    (2, 4, 16, 64, 32, 64, True),       # flat mode, 2 chunks
+    (1, 3, 12, 32, 64, 128, True),      # flat mode, 2 cout blocks, 4 chunks
+    (2, 2, 16, 16, 128, 16, True),      # deepest level geometry
+    (2, 1, 32, 128, 16, 16, False),     # 2-D (KD = 1), row mode
+    (1, 1, 20, 256, 32, 32, False),     # 2-D, two w-blocks, H not a multiple of R
+    (1, 6, 128, 128, 32, 32, True),     # > 148 work items: several items per persistent CTA (pipeline phases wrap)
+    (1, 5, 10, 24, 48, 48, True),       # odd sizes: W = 24, 48 channels (NB = 48)
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_conv_tcgen05_fwd_dgrad(case):
+    """tcgen05 implicit-GEMM conv (forward and, via the flipped pack, data-gradient) vs torch CPU fp32 conv on identical
+    bf16-representable operands: fp32 accumulate on both sides -> only the bf16 rounding of the OUTPUT differs (<= 2^-8 relative)."""
+    from ich_b200._lib import lib
+    n, d, h, w, cin, cout, k3d = case
+    kd = 3 if k3d else 1
+    assert lib().ich_conv_tc_supported(n, d, h, w, cin, cout, kd, 3, 3) == 1
+    assert lib().ich_conv_tc_supported(n, d, h, w, cout, cin, kd, 3, 3) == 1
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(n, cin, d, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(cout, cin, kd, 3, 3, generator=g) * 0.1).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    dy = torch.randn(n, cout, d, h, w, generator=g).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wt, b, padding=(1 if k3d else 0, 1, 1))
+    yr.backward(dy)
+    with config.override(precision='bf16', tensor_cores=True):
+        wg = wt.to(DEV)
+        y = ops.conv_forward(cl(x, torch.bfloat16), wg, b.to(DEV))
+        yrelu = ops.conv_forward(cl(x, torch.bfloat16), wg, b.to(DEV), relu=True)
+        dx = ops.conv_dgrad(cl(dy, torch.bfloat16), wg)
+    with config.override(precision='bf16', tensor_cores=False):
+        y_ffma = ops.conv_forward(cl(x, torch.bfloat16), wg, b.to(DEV))
+    torch.cuda.synchronize()
+    assert rel(nc(y), yr) < 4e-3, rel(nc(y), yr)
+    assert rel(nc(yrelu), F.relu(yr)) < 4e-3
+    assert rel(nc(dx), xr.grad) < 4e-3, rel(nc(dx), xr.grad)
+    # element-wise: never more than one bf16 ulp-ish away from the FFMA kernel's result (same operands, fp32 accumulate)
+    diff = (y.float() - y_ffma.float()).abs()
+    assert (diff <= 2e-2 * y_ffma.float().abs() + 1e-3).all(), diff.max().item()
