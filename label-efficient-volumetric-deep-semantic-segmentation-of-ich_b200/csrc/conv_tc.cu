@@ -408,10 +408,256 @@ int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float
   return ich_check_launch("ich_conv_tc_fwd");
 }
 
-int ich_conv_tc_wgrad_supported(int, int, int, int, int, int, int, int, int) { return 0; }
-int ich_conv_tc_wgrad(const void*, int, const void*, int, float*, int, int, int, int, int, int, int, int, int, void*) {
-  ich_set_error("ich_conv_tc_wgrad: not built");
-  return 1;
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Weight gradient on tensor cores.  dW[tap][ci][co] = sum_pos x[pos + shift(tap)][ci] * dy[pos][co].
+//   * K = voxel positions: both operands are MN-major (channels contiguous per position), no swizzle.
+//   * The x slab (KD planes x (R+2) rows x (WB+2) positions x CU channels) lands as [plane][chunk][row][pos][8]: 8-channel
+//     chunks are a uniform stride apart ACROSS planes, so the 128 MMA rows are (kd, ci) -- 3 planes x 32 channels = 96 live
+//     rows for 3-D layers; (kh, kw) are start-address shifts again -> 9 accumulators [128 x NB] in TMEM.
+//   * dy rows land without halo as [chunk][row][pos][8]; K runs over whole 16-position steps of each row, so no halo
+//     column is ever multiplied (no garbage in K).
+//   * persistent CTAs accumulate over all their positions in TMEM, then ONE epilogue adds the partial into dW with fp32
+//     atomics (split-K across CTAs).  Planes outside the volume are requested at an out-of-range coordinate -> TMA zero fill.
+// =====================================================================================================================
+namespace {
+
+struct WParams {
+  int N, D, H, W, Cin, Cout, KD;
+  int WB, PW, R, RB, CU, NB, chunks_u, chunks_v;
+  int n_wb, n_rb, n_cb, n_nb;
+  uint32_t plane_bytes, a_bytes, b_bytes, stage_bytes, tmem_cols;
+  long long n_pos_items;   // N * D * n_rb * n_wb
+  int splits;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int pair = blockIdx.y;
+  const int cb = pair / p.n_nb, nb = pair % p.n_nb;
+  const long long per = (p.n_pos_items + p.splits - 1) / p.splits;
+  const long long it_begin = (long long)blockIdx.x * per;
+  const long long it_end = it_begin + per < p.n_pos_items ? it_begin + per : p.n_pos_items;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long item = it_begin; item < it_end; ++item) {
+        long long t = item;
+        const int wb = (int)(t % p.n_wb); t /= p.n_wb;
+        const int rb = (int)(t % p.n_rb); t /= p.n_rb;
+        const int d = (int)(t % p.D); const int n = (int)(t / p.D);
+        const int w0 = wb * p.WB, h0 = rb * p.R;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+        uint8_t* sb = sa + p.a_bytes;
+        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+        for (int pl = 0; pl < p.KD; ++pl) {
+          const int dd = d + pl - (p.KD == 3 ? 1 : 0);
+          const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
+          tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - 1, h0 - 1, cb * p.chunks_u, coord);
+        }
+        tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * p.chunks_v, n * p.D + d);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // both operands MN-major (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = NB
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_sbo = (uint32_t)p.RB * p.PW * 16u;      // 8-channel chunk stride of x (uniform across planes)
+      const uint32_t b_sbo = (uint32_t)p.R * p.WB * 16u;       // 8-channel chunk stride of dy
+      int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      for (long long item = it_begin; item < it_end; ++item) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t sb = sa + p.a_bytes;
+        for (int r = 0; r < p.R; ++r)
+          for (int s16 = 0; s16 < p.WB; s16 += 16) {
+            const uint64_t bdesc = umma_desc(sb + (uint32_t)(r * p.WB + s16) * 16u, 128u, b_sbo);
+            for (int kh = 0; kh < 3; ++kh)
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint64_t adesc = umma_desc(sa + (uint32_t)((r + kh) * p.PW + s16 + kw) * 16u, 128u, a_sbo);
+                umma_bf16(tmem_base + (uint32_t)((kh * 3 + kw) * p.NB), adesc, bdesc, idesc, first ? 0u : 1u);
+              }
+            first = false;
+          }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&done_bar);
+    }
+  } else if (it_begin < it_end) {
+    // epilogue: TMEM lane = MMA row m = (kd, ci_local); 9 accumulators of NB columns
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int kd = m / p.CU, ci = cb * p.CU + (m % p.CU);
+    const bool valid = m < p.KD * p.CU;
+    const int taps = p.KD * 9;
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    for (int j = 0; j < 9; ++j) {
+      const int tap = kd * 9 + j;
+      for (int c0 = 0; c0 < p.NB; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.NB + c0), v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int co = nb * p.NB + c0 + k;
+            atomicAdd(&p.dw[((size_t)co * p.Cin + ci) * taps + tap], __uint_as_float(v[k]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+struct WPlan {
+  bool ok = false;
+  WParams p{};
+  size_t smem_bytes = 0;
+};
+
+WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
+  WPlan pl;
+  if (KH != 3 || KW != 3 || (KD != 1 && KD != 3)) return pl;
+  if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
+  if (N <= 0 || D <= 0 || H <= 0) return pl;
+  int WB;
+  if (W <= 128) WB = W;
+  else if (W % 128 == 0) WB = 128;
+  else return pl;
+  if (WB % 16) return pl;
+  const int PW = WB + 2;
+  int CU = 0;
+  const int cu_max = KD == 3 ? 32 : 128;
+  for (int c = cu_max; c >= 16; c -= 16)
+    if (Cin % c == 0) { CU = c; break; }
+  int NB = 0;
+  for (int c = 48; c >= 16; c -= 16)
+    if (Cout % c == 0) { NB = c; break; }
+  if (!CU || !NB) return pl;
+  const int chunks_u = CU / 8, chunks_v = NB / 8;
+  int bestR = 0;
+  size_t best_smem = 0;
+  for (int R = 1; R <= H + 1 && R <= 32; ++R) {
+    const int RB = R + 2;
+    if ((chunks_u * RB) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
+    size_t a = (size_t)KD * chunks_u * RB * PW * 16;
+    size_t b = (size_t)chunks_v * R * WB * 16;
+    size_t stage = (a + b + 1023) & ~(size_t)1023;
+    // the MMA always reads 16 chunks (128 rows): chunks beyond KD*chunks_u are garbage rows, but must stay inside the allocation
+    size_t over = (size_t)(16 - KD * chunks_u > 0 ? 16 - KD * chunks_u : 0) * RB * PW * 16 + (size_t)(2 * PW + 32) * 16;
+    size_t total = STAGES * stage + over + 1024;
+    if (total > SMEM_LIMIT) break;
+    bestR = R;
+    best_smem = total;
+  }
+  if (!bestR) return pl;
+  WParams& p = pl.p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD;
+  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2; p.CU = CU; p.NB = NB; p.chunks_u = chunks_u; p.chunks_v = chunks_v;
+  p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_cb = Cin / CU; p.n_nb = Cout / NB;
+  p.plane_bytes = (uint32_t)chunks_u * p.RB * PW * 16u;
+  p.a_bytes = (uint32_t)KD * p.plane_bytes;
+  p.b_bytes = (uint32_t)chunks_v * bestR * WB * 16u;
+  p.stage_bytes = (uint32_t)(((size_t)p.a_bytes + p.b_bytes + 1023) & ~(size_t)1023);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(9 * NB)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.n_pos_items = (long long)N * D * p.n_rb * p.n_wb;
+  const int pairs = p.n_cb * p.n_nb;
+  long long splits = (ich_num_sms() + pairs - 1) / pairs;
+  if (splits > p.n_pos_items) splits = p.n_pos_items;
+  if (splits < 1) splits = 1;
+  p.splits = (int)splits;
+  pl.smem_bytes = best_smem;
+  pl.ok = pairs <= 65535;
+  return pl;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ich_conv_tc_wgrad_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
+  if (!get_encode()) return 0;
+  return make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW).ok ? 1 : 0;
+}
+
+int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD, int KH,
+                      int KW, void* stream) {
+  WPlan pl = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW);
+  ICH_REQUIRE(pl.ok, "ich_conv_tc_wgrad: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
+  ICH_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
+              "ich_conv_tc_wgrad: pointers / pitches must be 16-byte aligned (x_ld %d, dy_ld %d)", x_ld, dy_ld);
+  EncodeTiledFn enc = get_encode();
+  ICH_REQUIRE(enc != nullptr, "ich_conv_tc_wgrad: cuTensorMapEncodeTiled not available");
+  WParams& p = pl.p;
+  p.dw = dw;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * KD * 9, s) != cudaSuccess) return ich_check_launch("ich_conv_tc_wgrad memset");
+
+  CUtensorMap map_x, map_dy;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  {
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)N * D};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, 16, (cuuint64_t)H * W * x_ld * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)p.chunks_u, 1};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_wgrad: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+  }
+  {
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 8), (cuuint64_t)N * D};
+    cuuint64_t strides[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, 16, (cuuint64_t)H * W * dy_ld * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.WB, (cuuint32_t)p.R, (cuuint32_t)p.chunks_v, 1};
+    CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_wgrad: cuTensorMapEncodeTiled(dy) failed with %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e != cudaSuccess) cudaGetLastError();
+    ICH_REQUIRE(e == cudaSuccess, "ich_conv_tc_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)p.splits, (unsigned)(p.n_cb * p.n_nb));
+  conv_tc_wgrad_kernel<<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
+  return ich_check_launch("ich_conv_tc_wgrad");
 }
 
 }  // extern "C"

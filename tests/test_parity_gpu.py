@@ -390,9 +390,15 @@ def test_conv_tcgen05_fwd_dgrad(case):
         y = ops.conv_forward(cl(x, torch.bfloat16), wg, b.to(DEV))
         yrelu = ops.conv_forward(cl(x, torch.bfloat16), wg, b.to(DEV), relu=True)
         dx = ops.conv_dgrad(cl(dy, torch.bfloat16), wg)
+        dw = ops.conv_wgrad(cl(x, torch.bfloat16), cl(dy, torch.bfloat16), wg)
+        if w % 16 == 0:
+            assert lib().ich_conv_tc_wgrad_supported(n, d, h, w, cin, cout, kd, 3, 3) == 1
     with config.override(precision='bf16', tensor_cores=False):
         y_ffma = ops.conv_forward(cl(x, torch.bfloat16), wg, b.to(DEV))
     torch.cuda.synchronize()
+    wref = wt.clone().requires_grad_(True)
+    F.conv3d(x, wref, None, padding=(1 if k3d else 0, 1, 1)).backward(dy)
+    assert rel(dw, wref.grad) < 1e-3, rel(dw, wref.grad)          # fp32 accumulate of exact bf16 products, fp32 output
     assert rel(nc(y), yr) < 4e-3, rel(nc(y), yr)
     assert rel(nc(yrelu), F.relu(yr)) < 4e-3
     assert rel(nc(dx), xr.grad) < 4e-3, rel(nc(dx), xr.grad)
