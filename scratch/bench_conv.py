@@ -1,0 +1,41 @@
+"""Per-layer conv micro-benchmark (cfg-3 shapes): CUDA-event timing of fwd / dgrad / wgrad through the C-ABI."""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests')); import conftest  # noqa
+import torch
+from ich_b200 import ops, config
+
+LAYERS = [  # name, N, D, H, W, Cin, Cout
+    ('d0.c2', 8, 64, 128, 128, 16, 32), ('u2.c1', 8, 64, 128, 128, 64, 32), ('u2.c2', 8, 64, 128, 128, 32, 32),
+    ('d1.c1', 8, 32, 64, 64, 32, 32), ('d1.c2', 8, 32, 64, 64, 32, 64), ('u1.c1', 8, 32, 64, 64, 128, 64), ('u1.c2', 8, 32, 64, 64, 64, 64),
+    ('d2.c2', 8, 16, 32, 32, 64, 128), ('u0.c1', 8, 16, 32, 32, 256, 128), ('u0.c2', 8, 16, 32, 32, 128, 128),
+    ('bt.c2', 8, 8, 16, 16, 128, 256),
+]
+only = sys.argv[1].split(',') if len(sys.argv) > 1 else None
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+config.set(precision='bf16')
+tot = {'fwd': [0, 0], 'dgrad': [0, 0], 'wgrad': [0, 0]}
+for name, n, d, h, w, cin, cout in LAYERS:
+    if only and name not in only:
+        continue
+    x = torch.randn(n, d, h, w, cin, device='cuda', dtype=torch.bfloat16)
+    dy = torch.randn(n, d, h, w, cout, device='cuda', dtype=torch.bfloat16)
+    wt = torch.randn(cout, cin, 3, 3, 3, device='cuda') * 0.05
+    flops = 2.0 * n * d * h * w * cin * cout * 27
+    res = []
+    for kind, fn in (('fwd', lambda: ops.conv_forward(x, wt, None)), ('dgrad', lambda: ops.conv_dgrad(dy, wt)),
+                     ('wgrad', lambda: ops.conv_wgrad(x, dy, wt))):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res.append(f'{kind} {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF/s')
+        tot[kind][0] += flops; tot[kind][1] += ms
+    print(f'{name} {n}x{d}x{h}x{w} {cin:3d}->{cout:3d} | ' + ' | '.join(res), flush=True)
+for k, (f, ms) in tot.items():
+    if ms:
+        print(f'total {k}: {ms:.2f} ms, {f / ms / 1e9:.1f} TF/s')
