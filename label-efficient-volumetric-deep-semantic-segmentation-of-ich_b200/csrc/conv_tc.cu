@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -67,6 +68,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -106,6 +113,33 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 
+// K-major SWIZZLE_32B descriptor: rows of 32 bytes (16 bf16 channels), 8-row groups SBO bytes apart.  Measured on B200
+// (scratch/swz_test.cu): the swizzle is applied to absolute shared-memory address bits, so the start address may be
+// shifted by ANY number of rows with base_offset = 0 -- which is what turns a conv tap into a pointer offset.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+
+// Warp-uniform single-lane election.  The issuing warps run their loops CONVERGED (all 32 lanes compute the same
+// descriptors, so the compiler keeps them in uniform registers) and only the UTCHMMA / UTMALDG / UTCBAR instructions are
+// predicated on the elected lane.  Issuing from inside an `if (lane == 0)` region instead makes ptxas wrap every MMA in an
+// ELECT / R2UR.BROADCAST waterfall loop: measured ~110 cycles per MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+
 struct Params {
   int N, D, H, W, Cin, Cout, KD;
   int WB, PW, R, RB, T, row_mode, NB;
@@ -117,6 +151,7 @@ struct Params {
   int y_ld;
   const float* bias;
   int relu;
+  int dbg;   // ablation switches for profiling only (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue stores
 };
 
 constexpr int STAGES = 2;
@@ -130,7 +165,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast from lane 0 so the compiler KNOWS the role index is warp-uniform (uniform branches + uniform datapath)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
@@ -148,8 +184,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const int planes_lo = (p.KD == 3) ? 1 : 0;     // slab plane 0 corresponds to d - planes_lo
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (warp-uniform loop, elected lane issues)
+    {
       int stage = 0; uint32_t phase = 0;
       for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         long long t = item;
@@ -162,21 +198,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_bytes;
-          mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
-          tma_load_5d(sa, &map_x, &full_bar[stage], 0, w0 - 1, h0 - 1, kc * 2, n * p.D + d - planes_lo);
-          tma_load_4d(sb, &map_w, &full_bar[stage], 0, nb * p.NB, kc * 2, 0);
+          if (elect_one()) {
+            if (p.dbg & 2) { mbar_arrive(&full_bar[stage]); }
+            else {
+              mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
+              tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + d - planes_lo);
+              tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb * p.NB, 0);
+            }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer (warp-uniform loop, elected lane issues)
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_lbo = (uint32_t)p.RB * p.PW * 16u;      // chunk (8-channel) stride inside a plane
-      const uint32_t a_plane = 2u * a_lbo;                     // plane stride (2 chunks per plane per stage)
-      const uint32_t b_lbo = (uint32_t)p.NB * 16u;
-      const uint32_t b_tap = 2u * b_lbo;
+      // The single issuing thread is the critical resource (measured: ~130 cycles per MMA when descriptors were rebuilt
+      // from scratch): keep the per-MMA work to two adds + one register pack.  Descriptor = {lo: start>>4 | LBO, hi: const}.
+      const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
+      const uint32_t plane16 = ((uint32_t)p.RB * p.PW * 32u) >> 4;       // plane stride in 16-byte units
+      const uint32_t row16 = ((uint32_t)p.PW * 32u) >> 4;                // one slab row
+      const uint32_t btap16 = ((uint32_t)p.NB * 32u) >> 4;               // one tap of the weight tile
+      const uint32_t tile16 = (p.row_mode ? (uint32_t)p.PW : 128u) * 2u; // M-tile step
+      const uint32_t NB = (uint32_t)p.NB;
+      const int T = p.T;
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
@@ -188,30 +235,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.T * p.NB);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T) * NB;
         for (int kc = 0; kc < p.KC; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + p.a_bytes;
-          bool first = (kc == 0);
-          for (int kd = kd_lo; kd <= kd_hi; ++kd)
-            for (int kh = 0; kh < 3; ++kh)
+          const uint32_t a_lo0 = (((sa & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)kd_lo * plane16;
+          uint32_t b_lo = ((((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)(kd_lo * 9) * btap16;
+          uint32_t accum = (kc == 0) ? 0u : 1u;
+          uint32_t a_kd = a_lo0;
+          for (int kd = kd_lo; kd <= kd_hi && !(p.dbg & 1); ++kd, a_kd += plane16) {
+            uint32_t a_kh = a_kd;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
+#pragma unroll
               for (int kw = 0; kw < 3; ++kw) {
-                const int tap = (kd * 3 + kh) * 3 + kw;
-                const uint64_t bdesc = umma_desc(sb + (uint32_t)tap * b_tap, b_lbo, 128u);
-                const uint32_t a_off = sa + (uint32_t)kd * a_plane + (uint32_t)(kh * p.PW + kw) * 16u;
-                for (int tt = 0; tt < p.T; ++tt) {
-                  const uint32_t base = p.row_mode ? (uint32_t)(tt * p.PW) : (uint32_t)(tt * 128);
-                  const uint64_t adesc = umma_desc(a_off + base * 16u, a_lbo, 128u);
-                  umma_bf16(d_tmem + (uint32_t)(tt * p.NB), adesc, bdesc, idesc, first ? 0u : 1u);
+                const uint64_t bdesc = pack64(b_lo, desc_hi);
+                b_lo += btap16;
+                uint32_t a_lo = a_kh + 2u * (uint32_t)kw;
+                uint32_t dcol = d_tmem;
+#pragma unroll 4
+                for (int tt = 0; tt < T; ++tt) {
+                  if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, idesc, accum);
+                  a_lo += tile16;
+                  dcol += NB;
                 }
-                first = false;
+                accum = 1u;
               }
-          umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
+            }
+          }
+          __syncwarp();
+          if (elect_one()) umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);                // accumulators complete
+        if (elect_one()) umma_commit(&tfull_bar[acc]);                // accumulators complete
+        __syncwarp();
       }
     }
   } else {
@@ -241,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           uint32_t v[16];
           tmem_ld16(taddr + (uint32_t)c0, v);
           tmem_ld_wait();
-          if (valid) {
+          if (valid && !(p.dbg & 4)) {
             float f32[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
@@ -372,26 +430,27 @@ int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float
   ICH_REQUIRE(enc != nullptr, "ich_conv_tc_fwd: cuTensorMapEncodeTiled not available");
   Params& p = pl.p;
   p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
+  { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
   CUtensorMap map_x, map_w;
   {
-    // x as (c8, W, H, C/8, N*D): the chunk dim makes the box land as [plane][chunk][row][pos][8ch]
-    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)N * D};
-    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, 16, (cuuint64_t)H * W * x_ld * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.RB, 2, (cuuint32_t)KD};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // x as (C, W, H, N*D): the box lands as [plane][row][pos][16 ch] = 32-byte rows, 32B-swizzled (full 32 B L2 sectors)
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
+    cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2};
+    cuuint32_t box[4] = {16, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)KD};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_fwd: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
   }
   {
-    // w [taps][Cout][Cin] as (c8, Cout, Cin/8, taps)
-    cuuint64_t dims[4] = {8, (cuuint64_t)Cout, (cuuint64_t)(Cin / 8), (cuuint64_t)p.taps};
-    cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)Cout * Cin * 2};
-    cuuint32_t box[4] = {8, (cuuint32_t)p.NB, 2, (cuuint32_t)p.taps};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    // w [taps][Cout][Cin] as (Cin, Cout, taps): box = [tap][NB rows][16 ch], same 32-byte swizzled rows
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)p.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[3] = {16, (cuuint32_t)p.NB, (cuuint32_t)p.taps};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_fwd: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
   }
@@ -440,7 +499,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
   __shared__ uint32_t tmem_base_smem;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast from lane 0 so the compiler KNOWS the role index is warp-uniform (uniform branches + uniform datapath)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
@@ -462,7 +522,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   const long long it_end = it_begin + per < p.n_pos_items ? it_begin + per : p.n_pos_items;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (long long item = it_begin; item < it_end; ++item) {
         long long t = item;
@@ -473,43 +533,57 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
         uint8_t* sb = sa + p.a_bytes;
-        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-        for (int pl = 0; pl < p.KD; ++pl) {
-          const int dd = d + pl - (p.KD == 3 ? 1 : 0);
-          const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
-          tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - 1, h0 - 1, cb * p.chunks_u, coord);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+          for (int pl = 0; pl < p.KD; ++pl) {
+            const int dd = d + pl - (p.KD == 3 ? 1 : 0);
+            const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
+            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - 1, h0 - 1, cb * p.chunks_u, coord);
+          }
+          tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * p.chunks_v, n * p.D + d);
         }
-        tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * p.chunks_v, n * p.D + d);
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // both operands MN-major (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = NB
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_sbo = (uint32_t)p.RB * p.PW * 16u;      // 8-channel chunk stride of x (uniform across planes)
-      const uint32_t b_sbo = (uint32_t)p.R * p.WB * 16u;       // 8-channel chunk stride of dy
+      // descriptor = {lo: start>>4 | (LBO = 128 B)<<16, hi: SBO>>4 | version}; per MMA only `lo` changes (one add + one pack)
+      const uint32_t a_hi = (((uint32_t)p.RB * p.PW * 16u) >> 4) | (1u << 14);   // SBO = 8-channel chunk stride of x (uniform across planes)
+      const uint32_t b_hi = (((uint32_t)p.R * p.WB * 16u) >> 4) | (1u << 14);    // SBO = 8-channel chunk stride of dy
+      const uint32_t PW = (uint32_t)p.PW, WB = (uint32_t)p.WB, NB = (uint32_t)p.NB;
       int stage = 0; uint32_t phase = 0;
-      bool first = true;
+      uint32_t accum = 0u;
       for (long long item = it_begin; item < it_end; ++item) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        const uint32_t sb = sa + p.a_bytes;
-        for (int r = 0; r < p.R; ++r)
-          for (int s16 = 0; s16 < p.WB; s16 += 16) {
-            const uint64_t bdesc = umma_desc(sb + (uint32_t)(r * p.WB + s16) * 16u, 128u, b_sbo);
-            for (int kh = 0; kh < 3; ++kh)
+        uint32_t a_row = ((sa & 0x3FFFFu) >> 4) | (8u << 16);                      // one position = 16 B = 1 unit
+        uint32_t b_row = (((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (8u << 16);
+        for (int r = 0; r < p.R; ++r, a_row += PW, b_row += WB) {
+          for (uint32_t s16 = 0; s16 < WB; s16 += 16) {
+            const uint64_t bdesc = pack64(b_row + s16, b_hi);
+            uint32_t a_kh = a_row + s16;
+            uint32_t dcol = tmem_base;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh, a_kh += PW) {
+#pragma unroll
               for (int kw = 0; kw < 3; ++kw) {
-                const uint64_t adesc = umma_desc(sa + (uint32_t)((r + kh) * p.PW + s16 + kw) * 16u, 128u, a_sbo);
-                umma_bf16(tmem_base + (uint32_t)((kh * 3 + kw) * p.NB), adesc, bdesc, idesc, first ? 0u : 1u);
+                if (elect_one()) umma_bf16(dcol, pack64(a_kh + (uint32_t)kw, a_hi), bdesc, idesc, accum);
+                dcol += NB;
               }
-            first = false;
+            }
+            accum = 1u;
           }
-        umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&done_bar);
+      if (elect_one()) umma_commit(&done_bar);
+      __syncwarp();
     }
   } else if (it_begin < it_end) {
     // epilogue: TMEM lane = MMA row m = (kd, ci_local); 9 accumulators of NB columns
