@@ -44,10 +44,22 @@ int ich_conv_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, int dtype
 int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
 int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
                     int Cin, int Cout, int KD, int KH, int KW, int relu, void* stream);
-/* weight gradient on tensor cores; dw in torch layout [Cout][Cin][taps] fp32; workspace: see ich_conv_tc_wgrad_workspace */
+/* transposed conv k2 s2 on tensor cores (same call site as ich_convT2_fwd): 1x1 GEMM + depth-to-space scatter epilogue.
+ * wpack_bf16 = [taps*Cout][Cin] bf16.  Grid args = the COARSE grid.                                                   */
+int ich_convT2_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int FD);
+int ich_convT2_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
+                      int Cin, int Cout, int FD, void* stream);
+/* weight gradient on tensor cores; dw in torch layout [Cout][Cin][taps] fp32 */
 int ich_conv_tc_wgrad_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
 int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout,
                       int KD, int KH, int KW, void* stream);
+/* transposed-conv weight gradient on tensor cores: g = ich_space_to_depth2 of the up-sampled gradient ([voxel][tap*Cout+co]);
+ * dw in torch layout [Cin][Cout][taps] fp32.  Grid args = the COARSE grid.                                               */
+int ich_convT2_tc_wgrad_supported(int N, int D, int H, int W, int Cin, int Cout, int FD);
+int ich_convT2_tc_wgrad(const void* x, int x_ld, const void* g, int g_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int FD,
+                        void* stream);
+/* fine grid [2x voxels][C] (pitch src_ld) -> coarse grid [voxel][tap*C + c], tap = (i<<2)|(j<<1)|l; backward of ConvTranspose k2 s2 */
+int ich_space_to_depth2(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
 
 /* ---- transposed conv k2 s2: nn.ConvTranspose3d/2d (models/networks/UNet.py:75-76). Grid args = the COARSE grid;
  *      FD = depth factor (2 for 3-D, 1 for 2-D). wpack = [Cin][taps*Cout], wpack_d = [taps*Cout][Cin], taps = 4*FD.     */

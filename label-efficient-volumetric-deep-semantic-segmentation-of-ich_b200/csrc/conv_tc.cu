@@ -141,8 +141,9 @@ __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
 }
 
 struct Params {
-  int N, D, H, W, Cin, Cout, KD;
+  int N, D, H, W, Cin, Cout, KD, KS;   // KS = in-plane kernel size (3, or 1 for 1x1 / transposed-conv GEMMs)
   int WB, PW, R, RB, T, row_mode, NB;
+  int up_fd, up_cout;                  // transposed-conv scatter epilogue: depth factor (0 = off) and its Cout
   int n_wb, n_rb, n_nb, KC, taps;
   int nacc;
   uint32_t a_bytes, a_tx_bytes, b_bytes, stage_bytes, tmem_cols;
@@ -157,6 +158,7 @@ struct Params {
 constexpr int STAGES = 2;
 constexpr int NUM_THREADS = 192;
 
+template <int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -202,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             if (p.dbg & 2) { mbar_arrive(&full_bar[stage]); }
             else {
               mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
-              tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + d - planes_lo);
+              tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - KS / 2, h0 - KS / 2, n * p.D + d - planes_lo);
               tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb * p.NB, 0);
             }
           }
@@ -241,15 +243,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t a_lo0 = (((sa & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)kd_lo * plane16;
-          uint32_t b_lo = ((((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)(kd_lo * 9) * btap16;
+          uint32_t b_lo = ((((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)(kd_lo * KS * KS) * btap16;
           uint32_t accum = (kc == 0) ? 0u : 1u;
           uint32_t a_kd = a_lo0;
           for (int kd = kd_lo; kd <= kd_hi && !(p.dbg & 1); ++kd, a_kd += plane16) {
             uint32_t a_kh = a_kd;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
+            for (int kh = 0; kh < KS; ++kh, a_kh += row16) {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
+              for (int kw = 0; kw < KS; ++kw) {
                 const uint64_t bdesc = pack64(b_lo, desc_hi);
                 b_lo += btap16;
                 uint32_t a_lo = a_kh + 2u * (uint32_t)kw;
@@ -292,8 +294,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int f = (p.row_mode ? tt * p.PW : tt * 128) + l;
         const int r = f / p.PW, pos = f - r * p.PW;
         const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W);
-        const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
-        bf16* yrow = p.y + vox * p.y_ld + n0;
+        long long vox;
+        int bias0 = n0;
+        if (p.up_fd) {   // transposed conv k2 s2: this cout block belongs to one tap (i, j, l) -> scatter to the fine grid
+          const int tap = n0 / p.up_cout;
+          bias0 = n0 - tap * p.up_cout;
+          const int ti = tap >> 2, tj = (tap >> 1) & 1, tl = tap & 1;
+          vox = ((((long long)n * p.D + d) * p.up_fd + ti) * (2 * p.H) + (2 * (h0 + r) + tj)) * (2 * p.W) + (2 * (w0 + pos) + tl);
+        } else {
+          vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
+        }
+        bf16* yrow = p.y + vox * p.y_ld + bias0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
         for (int c0 = 0; c0 < p.NB; c0 += 16) {
           uint32_t v[16];
@@ -304,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
               float a = __uint_as_float(v[k]);
-              if (p.bias) a += p.bias[n0 + c0 + k];
+              if (p.bias) a += p.bias[bias0 + c0 + k];
               if (p.relu) a = fmaxf(a, 0.f);
               f32[k] = a;
             }
@@ -351,21 +362,22 @@ struct Plan {
 
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 4096;   // dynamic limit: leave room for the static barriers / alignment
 
-Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
+Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, int nb_must_divide = 0) {
   Plan pl;
-  if (KH != 3 || KW != 3 || (KD != 1 && KD != 3)) return pl;
+  if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
+  const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
   if (N <= 0 || D <= 0 || H <= 0 || W < 4) return pl;
   int WB;
   if (W <= 128) WB = W;
   else if (W % 128 == 0) WB = 128;
   else return pl;
-  const int PW = WB + 2;
+  const int PW = WB + 2 * hw;
   int NB = 0;
   for (int c = 64; c >= 16; c -= 16)
-    if (Cout % c == 0) { NB = c; break; }
+    if (Cout % c == 0 && (!nb_must_divide || nb_must_divide % c == 0)) { NB = c; break; }
   if (!NB) return pl;
-  const int taps = KD * 9;
+  const int taps = KD * KS * KS;
   const uint32_t b_bytes = (uint32_t)taps * 2u * NB * 16u;
   const bool row_mode = (WB == 128);
   long long best_cost = -1;
@@ -373,7 +385,7 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   size_t best_smem = 0;
   uint32_t best_a = 0;
   for (int R = 1; R <= H && R <= 64; ++R) {
-    const int RB = R + 2;
+    const int RB = R + 2 * hw;
     const int T = row_mode ? R : (((R - 1) * PW + WB) + 127) / 128;
     int nacc = 0;
     if (2 * T * NB <= 512) nacc = 2;
@@ -381,7 +393,7 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
     else continue;
     uint32_t a_bytes = (uint32_t)KD * 2u * RB * PW * 16u;
     a_bytes = (a_bytes + 127u) & ~127u;
-    long long over = row_mode ? 0 : ((long long)(128 * T + 2 * PW + 2) - (long long)RB * PW) * 16;
+    long long over = row_mode ? 0 : ((long long)(128 * T + 2 * hw * PW + 2 * hw) - (long long)RB * PW) * 32;
     if (over < 0) over = 0;
     size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
     size_t total = STAGES * stage + (size_t)over + 1024;   // +1024: manual alignment of the dynamic base
@@ -394,8 +406,9 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   }
   if (best_cost < 0) return pl;
   Params& p = pl.p;
-  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD;
-  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2; p.T = bestT; p.row_mode = row_mode; p.NB = NB;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
+  p.up_fd = 0; p.up_cout = 0;
+  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hw; p.T = bestT; p.row_mode = row_mode; p.NB = NB;
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / 16; p.taps = taps;
   p.nacc = bestAcc;
   p.a_bytes = best_a;
@@ -420,15 +433,14 @@ int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD,
   return make_plan(N, D, H, W, Cin, Cout, KD, KH, KW).ok ? 1 : 0;
 }
 
-int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W, int Cin,
-                    int Cout, int KD, int KH, int KW, int relu, void* stream) {
-  Plan pl = make_plan(N, D, H, W, Cin, Cout, KD, KH, KW);
-  ICH_REQUIRE(pl.ok, "ich_conv_tc_fwd: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
-  ICH_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wpack_bf16 & 15) == 0,
-              "ich_conv_tc_fwd: pointers / pitches must be 16-byte aligned (x_ld %d, y_ld %d)", x_ld, y_ld);
-  EncodeTiledFn enc = get_encode();
-  ICH_REQUIRE(enc != nullptr, "ich_conv_tc_fwd: cuTensorMapEncodeTiled not available");
+static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int relu,
+                          cudaStream_t stream, const char* what) {
   Params& p = pl.p;
+  const int N = p.N, D = p.D, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout, KD = p.KD;
+  ICH_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wpack_bf16 & 15) == 0,
+              "%s: pointers / pitches must be 16-byte aligned (x_ld %d, y_ld %d)", what, x_ld, y_ld);
+  EncodeTiledFn enc = get_encode();
+  ICH_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled not available", what);
   p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
   { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
 
@@ -441,7 +453,7 @@ int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_fwd: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(x) failed with %d", what, (int)r);
   }
   {
     // w [taps][Cout][Cin] as (Cin, Cout, taps): box = [tap][NB rows][16 ch], same 32-byte swizzled rows
@@ -452,21 +464,46 @@ int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float
     CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_fwd: cuTensorMapEncodeTiled(w) failed with %d", (int)r);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(w) failed with %d", what, (int)r);
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e != cudaSuccess) cudaGetLastError();
-    ICH_REQUIRE(e == cudaSuccess, "ich_conv_tc_fwd: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    ICH_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr_set = true;
   }
   long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
-  size_t smem = pl.smem_bytes;
-  conv_tc_kernel<<<(unsigned)grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(map_x, map_w, p);
-  return ich_check_launch("ich_conv_tc_fwd");
+  if (p.KS == 3) conv_tc_kernel<3><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else conv_tc_kernel<1><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  return ich_check_launch(what);
 }
 
+int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W, int Cin,
+                    int Cout, int KD, int KH, int KW, int relu, void* stream) {
+  Plan pl = make_plan(N, D, H, W, Cin, Cout, KD, KH, KW);
+  ICH_REQUIRE(pl.ok, "ich_conv_tc_fwd: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
+  return launch_conv_tc(pl, x, x_ld, wpack_bf16, bias, y, y_ld, relu, (cudaStream_t)stream, "ich_conv_tc_fwd");
+}
+
+// Transposed conv k2 s2 on tensor cores: a 1x1 GEMM [voxels x Cin] x [Cin x taps*Cout] whose epilogue scatters every
+// (tap, cout-block) to the fine grid (depth-to-space) -- straight into the channel slab of the concat buffer.
+// wpack_bf16 = [taps*Cout][Cin] bf16 (row n = tap*Cout + co), taps = 4*FD.  Grid args = the COARSE grid.
+int ich_convT2_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int FD) {
+  if (!get_encode() || (FD != 1 && FD != 2) || Cout % 16) return 0;
+  return make_plan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1, Cout).ok ? 1 : 0;
+}
+
+int ich_convT2_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W, int Cin,
+                      int Cout, int FD, void* stream) {
+  ICH_REQUIRE((FD == 1 || FD == 2) && Cout % 16 == 0, "ich_convT2_tc_fwd: unsupported FD %d / Cout %d", FD, Cout);
+  Plan pl = make_plan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1, Cout);
+  ICH_REQUIRE(pl.ok, "ich_convT2_tc_fwd: unsupported shape N%d D%d H%d W%d Cin%d Cout%d", N, D, H, W, Cin, Cout);
+  pl.p.up_fd = FD;
+  pl.p.up_cout = Cout;
+  return launch_conv_tc(pl, x, x_ld, wpack_bf16, bias, y, y_ld, 0, (cudaStream_t)stream, "ich_convT2_tc_fwd");
+}
 
 }  // extern "C"
 
@@ -484,7 +521,8 @@ int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float
 namespace {
 
 struct WParams {
-  int N, D, H, W, Cin, Cout, KD;
+  int N, D, H, W, Cin, Cout, KD, KS;
+  int out_mode, up_cout, taps_out;   // out_mode 1: transposed-conv layout dW[ci][co][tap], columns n = tap*up_cout + co
   int WB, PW, R, RB, CU, NB, chunks_u, chunks_v;
   int n_wb, n_rb, n_cb, n_nb;
   uint32_t plane_bytes, a_bytes, b_bytes, stage_bytes, tmem_cols;
@@ -493,6 +531,7 @@ struct WParams {
   float* dw;
 };
 
+template <int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -538,7 +577,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           for (int pl = 0; pl < p.KD; ++pl) {
             const int dd = d + pl - (p.KD == 3 ? 1 : 0);
             const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
-            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - 1, h0 - 1, cb * p.chunks_u, coord);
+            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2, cb * p.chunks_u, coord);
           }
           tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * p.chunks_v, n * p.D + d);
         }
@@ -568,9 +607,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             uint32_t a_kh = a_row + s16;
             uint32_t dcol = tmem_base;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh, a_kh += PW) {
+            for (int kh = 0; kh < KS; ++kh, a_kh += PW) {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
+              for (int kw = 0; kw < KS; ++kw) {
                 if (elect_one()) umma_bf16(dcol, pack64(a_kh + (uint32_t)kw, a_hi), bdesc, idesc, accum);
                 dcol += NB;
               }
@@ -591,11 +630,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int m = q * 32 + lane;
     const int kd = m / p.CU, ci = cb * p.CU + (m % p.CU);
     const bool valid = m < p.KD * p.CU;
-    const int taps = p.KD * 9;
+    const int taps = p.KD * KS * KS;
     mbar_wait(&done_bar, 0);
     tc_fence_after();
-    for (int j = 0; j < 9; ++j) {
-      const int tap = kd * 9 + j;
+    for (int j = 0; j < KS * KS; ++j) {
+      const int tap = kd * KS * KS + j;
       for (int c0 = 0; c0 < p.NB; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.NB + c0), v);
@@ -603,8 +642,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (valid) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const int co = nb * p.NB + c0 + k;
-            atomicAdd(&p.dw[((size_t)co * p.Cin + ci) * taps + tap], __uint_as_float(v[k]));
+            const int col = nb * p.NB + c0 + k;
+            size_t idx;
+            if (p.out_mode == 0) idx = ((size_t)col * p.Cin + ci) * taps + tap;                    // conv: dW[co][ci][tap]
+            else { const int t2 = col / p.up_cout; idx = ((size_t)ci * p.up_cout + (col - t2 * p.up_cout)) * p.taps_out + t2; }   // convT: dW[ci][co][tap]
+            atomicAdd(&p.dw[idx], __uint_as_float(v[k]));
           }
         }
       }
@@ -626,7 +668,8 @@ struct WPlan {
 
 WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
   WPlan pl;
-  if (KH != 3 || KW != 3 || (KD != 1 && KD != 3)) return pl;
+  if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
+  const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
   if (N <= 0 || D <= 0 || H <= 0) return pl;
   int WB;
@@ -634,20 +677,20 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   else if (W % 128 == 0) WB = 128;
   else return pl;
   if (WB % 16) return pl;
-  const int PW = WB + 2;
+  const int PW = WB + 2 * hw;
   int CU = 0;
   const int cu_max = KD == 3 ? 32 : 128;
   for (int c = cu_max; c >= 16; c -= 16)
     if (Cin % c == 0) { CU = c; break; }
   int NB = 0;
-  for (int c = 48; c >= 16; c -= 16)
+  for (int c = (KS == 1 ? 256 : 48); c >= 16; c -= 16)   // KS*KS accumulators of NB columns must fit 512 TMEM columns
     if (Cout % c == 0) { NB = c; break; }
   if (!CU || !NB) return pl;
   const int chunks_u = CU / 8, chunks_v = NB / 8;
   int bestR = 0;
   size_t best_smem = 0;
   for (int R = 1; R <= H + 1 && R <= 32; ++R) {
-    const int RB = R + 2;
+    const int RB = R + 2 * hw;
     if ((chunks_u * RB) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
     size_t a = (size_t)KD * chunks_u * RB * PW * 16;
     size_t b = (size_t)chunks_v * R * WB * 16;
@@ -661,15 +704,16 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   }
   if (!bestR) return pl;
   WParams& p = pl.p;
-  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD;
-  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2; p.CU = CU; p.NB = NB; p.chunks_u = chunks_u; p.chunks_v = chunks_v;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
+  p.out_mode = 0; p.up_cout = 0; p.taps_out = 0;
+  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hw; p.CU = CU; p.NB = NB; p.chunks_u = chunks_u; p.chunks_v = chunks_v;
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_cb = Cin / CU; p.n_nb = Cout / NB;
   p.plane_bytes = (uint32_t)chunks_u * p.RB * PW * 16u;
   p.a_bytes = (uint32_t)KD * p.plane_bytes;
   p.b_bytes = (uint32_t)chunks_v * bestR * WB * 16u;
   p.stage_bytes = (uint32_t)(((size_t)p.a_bytes + p.b_bytes + 1023) & ~(size_t)1023);
   uint32_t cols = 32;
-  while (cols < (uint32_t)(9 * NB)) cols <<= 1;
+  while (cols < (uint32_t)(KS * KS * NB)) cols <<= 1;
   p.tmem_cols = cols;
   p.n_pos_items = (long long)N * D * p.n_rb * p.n_wb;
   const int pairs = p.n_cb * p.n_nb;
@@ -691,18 +735,16 @@ int ich_conv_tc_wgrad_supported(int N, int D, int H, int W, int Cin, int Cout, i
   return make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW).ok ? 1 : 0;
 }
 
-int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD, int KH,
-                      int KW, void* stream) {
-  WPlan pl = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW);
-  ICH_REQUIRE(pl.ok, "ich_conv_tc_wgrad: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
-  ICH_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
-              "ich_conv_tc_wgrad: pointers / pitches must be 16-byte aligned (x_ld %d, dy_ld %d)", x_ld, dy_ld);
-  EncodeTiledFn enc = get_encode();
-  ICH_REQUIRE(enc != nullptr, "ich_conv_tc_wgrad: cuTensorMapEncodeTiled not available");
+static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* dy, int dy_ld, float* dw, size_t dw_elems, cudaStream_t s,
+                                const char* what) {
   WParams& p = pl.p;
+  const int N = p.N, D = p.D, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout;
+  ICH_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
+              "%s: pointers / pitches must be 16-byte aligned (x_ld %d, dy_ld %d)", what, x_ld, dy_ld);
+  EncodeTiledFn enc = get_encode();
+  ICH_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled not available", what);
   p.dw = dw;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * KD * 9, s) != cudaSuccess) return ich_check_launch("ich_conv_tc_wgrad memset");
+  if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_elems, s) != cudaSuccess) return ich_check_launch(what);
 
   CUtensorMap map_x, map_dy;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -712,7 +754,7 @@ int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float*
     cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)p.chunks_u, 1};
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_wgrad: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(x) failed with %d", what, (int)r);
   }
   {
     cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 8), (cuuint64_t)N * D};
@@ -720,18 +762,44 @@ int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float*
     cuuint32_t box[5] = {8, (cuuint32_t)p.WB, (cuuint32_t)p.R, (cuuint32_t)p.chunks_v, 1};
     CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ICH_REQUIRE(r == CUDA_SUCCESS, "ich_conv_tc_wgrad: cuTensorMapEncodeTiled(dy) failed with %d", (int)r);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy) failed with %d", what, (int)r);
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e != cudaSuccess) cudaGetLastError();
-    ICH_REQUIRE(e == cudaSuccess, "ich_conv_tc_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    ICH_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((unsigned)p.splits, (unsigned)(p.n_cb * p.n_nb));
-  conv_tc_wgrad_kernel<<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
-  return ich_check_launch("ich_conv_tc_wgrad");
+  if (p.KS == 3) conv_tc_wgrad_kernel<3><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
+  else conv_tc_wgrad_kernel<1><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
+  return ich_check_launch(what);
+}
+
+int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD, int KH,
+                      int KW, void* stream) {
+  WPlan pl = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW);
+  ICH_REQUIRE(pl.ok, "ich_conv_tc_wgrad: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
+  return launch_conv_tc_wgrad(pl, x, x_ld, dy, dy_ld, dw, (size_t)Cout * Cin * KD * KH * KW, (cudaStream_t)stream, "ich_conv_tc_wgrad");
+}
+
+// Transposed conv k2 s2 weight gradient: g = the up-sampled gradient re-packed to the coarse grid by ich_space_to_depth2
+// ([voxel][tap*Cout + co]); dW[ci][co][tap] = sum_v x[v][ci] * g[v][tap*Cout + co]  (a 1x1 weight-gradient GEMM).
+int ich_convT2_tc_wgrad_supported(int N, int D, int H, int W, int Cin, int Cout, int FD) {
+  if (!get_encode() || (FD != 1 && FD != 2)) return 0;
+  return make_wplan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1).ok ? 1 : 0;
+}
+
+int ich_convT2_tc_wgrad(const void* x, int x_ld, const void* g, int g_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int FD,
+                        void* stream) {
+  WPlan pl = make_wplan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1);
+  ICH_REQUIRE(pl.ok && (FD == 1 || FD == 2), "ich_convT2_tc_wgrad: unsupported shape N%d D%d H%d W%d Cin%d Cout%d FD%d", N, D, H, W, Cin, Cout, FD);
+  pl.p.out_mode = 1;
+  pl.p.up_cout = Cout;
+  pl.p.taps_out = 4 * FD;
+  return launch_conv_tc_wgrad(pl, x, x_ld, g, g_ld, dw, (size_t)Cin * Cout * 4 * FD, (cudaStream_t)stream, "ich_convT2_tc_wgrad");
 }
 
 }  // extern "C"

@@ -365,6 +365,28 @@ __global__ void __launch_bounds__(256) slab_copy_kernel(const T* __restrict__ sr
   }
 }
 
+
+// ---- space-to-depth (2x; depth factor FD): fine [N][FD*D][2H][2W][C] (pitch ld) -> coarse [N][D][H][W][taps*C] --------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const T* __restrict__ src, int s_ld, T* __restrict__ dst, int N, int D, int H, int W, int C,
+                                                             int FD) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V, taps = 4 * FD;
+  const long long total = (long long)N * D * H * W * taps * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % groups); long long t = i / groups;
+    int tap = (int)(t % taps); t /= taps;            // t = coarse voxel
+    int w = (int)(t % W); long long u = t / W;
+    int h = (int)(u % H); long long r = u / H;       // r = n*D + d
+    int ti = tap >> 2, tj = (tap >> 1) & 1, tl = tap & 1;
+    long long fine = ((r * FD + ti) * (2 * H) + (2 * h + tj)) * (2LL * W) + (2 * w + tl);
+    const T* sp = src + fine * s_ld + g * V;
+    T* dp = dst + (t * taps + tap) * (long long)C + g * V;
+    if (VEC) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
+    else *dp = *sp;
+  }
+}
+
 // ---- global average pool over the voxels of each sample: x [N][S][C] -> out fp32 [N][C]; and its backward -----------
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ x, int ld, float* __restrict__ out, long long S, int C) {
@@ -520,6 +542,20 @@ int ich_slab_copy(const void* src, int src_ld, void* dst, int dst_ld, int dtype,
       slab_copy_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, dst_ld, M, C);
   })
   return ich_check_launch("ich_slab_copy");
+}
+
+int ich_space_to_depth2(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(FD == 1 || FD == 2, "ich_space_to_depth2: FD must be 1 or 2");
+  long long total = (long long)N * D * H * W * 4 * FD * C;
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, "ich_space_to_depth2", {
+    if (vec_ok<T>(src, src_ld, C) && vec_ok<T>(dst, C, C))
+      space_to_depth_kernel<T, true><<<grid_for(total / Vec<T>::N, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, N, D, H, W, C, FD);
+    else
+      space_to_depth_kernel<T, false><<<grid_for(total, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, N, D, H, W, C, FD);
+  })
+  return ich_check_launch("ich_space_to_depth2");
 }
 
 int ich_avgpool_fwd(const void* x, int ld, int dtype, float* out, int N, long long S, int C, void* stream) {

@@ -127,6 +127,65 @@ __global__ void __launch_bounds__(256) head1_bwd_kernel(const T* __restrict__ x,
   if (threadIdx.x == 0 && db) atomicAdd(db, red[HEAD_MAX_CIN]);
 }
 
+
+// Vectorised variant for the shipped head (Cout == 1, Cin a multiple of the 16-byte vector, aligned rows): one voxel per
+// thread per iteration, 16-byte loads of x and stores of dx, Cin register accumulators reduced once per block.
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) head1_bwd_vec_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w, const float* __restrict__ out,
+                                                            const float* __restrict__ dout, T* __restrict__ dx, int dx_ld, float* __restrict__ dw,
+                                                            float* __restrict__ db, long long M, int act, int need_dx) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float red[CIN + 1];
+  float wreg[CIN], gw[CIN];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) { wreg[c] = w[c]; gw[c] = 0.f; }
+  for (int i = threadIdx.x; i <= CIN; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float gb = 0.f;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    float p = out[m], g = dout[m];
+    float dl = act == 1 ? g * p * (1.f - p) : g;
+    gb += dl;
+    const T* row = x + m * x_ld;
+#pragma unroll
+    for (int c = 0; c < CIN; c += V) {
+      float v[V], o[V];
+      Vec<T>::load(row + c, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { gw[c + k] = fmaf(dl, v[k], gw[c + k]); o[k] = dl * wreg[c + k]; }
+      if (need_dx) Vec<T>::store(dx + m * dx_ld + c, o);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CIN; ++c) {
+    float v = warp_sum(gw[c]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[c], v);
+  }
+  gb = warp_sum(gb);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&red[CIN], gb);
+  __syncthreads();
+  for (int c = threadIdx.x; c < CIN; c += blockDim.x) atomicAdd(&dw[c], red[c]);
+  if (threadIdx.x == 0 && db) atomicAdd(db, red[CIN]);
+}
+
+template <typename T>
+bool head1_bwd_vec_launch(const T* x, int x_ld, const float* w, const float* out, const float* dout, T* dx, int dx_ld, float* dw, float* db,
+                          long long M, int Cin, int act, cudaStream_t s) {
+  const bool aligned = (x_ld % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                       (!dx || ((dx_ld % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(dx) & 15) == 0)));
+  if (!aligned) return false;
+  int grid = grid_for(M, 256, 4);
+#define ICH_H1(C) head1_bwd_vec_kernel<T, C><<<grid, 256, 0, s>>>(x, x_ld, w, out, dout, dx, dx_ld, dw, db, M, act, dx != nullptr)
+  switch (Cin) {
+    case 8: if (Vec<T>::N <= 8) { ICH_H1(8); return true; } return false;
+    case 16: ICH_H1(16); return true;
+    case 32: ICH_H1(32); return true;
+    case 64: ICH_H1(64); return true;
+    default: return false;
+  }
+#undef ICH_H1
+}
+
 // ---- soft-Dice / Dice+BCE ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float powp(float v, float P) { return P == 1.f ? v : P == 2.f ? v * v : powf(v, P); }
 __device__ __forceinline__ float dpowp(float v, float P) { return P == 1.f ? 1.f : P == 2.f ? 2.f * v : P * powf(v, P - 1.f); }
@@ -402,6 +461,10 @@ int ich_head1_bwd(const void* x, int x_ld, int dtype, const float* w, const floa
   cudaMemsetAsync(dw, 0, sizeof(float) * Cin, s);
   if (db) cudaMemsetAsync(db, 0, sizeof(float), s);
   if (M == 0) return 0;
+  if (dtype == ICH_F32 && head1_bwd_vec_launch<float>((const float*)x, x_ld, w, out, dout, (float*)dx, dx_ld, dw, db, M, Cin, act, s))
+    return ich_check_launch("ich_head1_bwd");
+  if (dtype == ICH_BF16 && head1_bwd_vec_launch<bf16>((const bf16*)x, x_ld, w, out, dout, (bf16*)dx, dx_ld, dw, db, M, Cin, act, s))
+    return ich_check_launch("ich_head1_bwd");
   int grid = grid_for(M, 256, 4);
   if (dtype == ICH_F32) head1_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)x, x_ld, w, out, dout, (float*)dx, dx_ld, dw, db, M, Cin, act, dx != nullptr);
   else if (dtype == ICH_BF16) head1_bwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, x_ld, w, out, dout, (bf16*)dx, dx_ld, dw, db, M, Cin, act, dx != nullptr);

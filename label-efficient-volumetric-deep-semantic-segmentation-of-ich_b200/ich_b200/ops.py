@@ -75,6 +75,10 @@ def _pack(param, kind):
                 packs[kind] = w.permute(2, 3, 4, 0, 1).reshape(-1, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
             elif kind == 'conv_dgrad_tc':  # [taps'][Cin][Cout] bf16
                 packs[kind] = w.flip(2, 3, 4).permute(2, 3, 4, 1, 0).reshape(-1, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
+            elif kind == 'convT_fwd_tc':  # [taps*Cout][Cin] bf16 (B operand of the up-sampling GEMM)
+                packs[kind] = w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).to(torch.bfloat16).contiguous()
+            elif kind == 'convT_dgrad_tc':  # [Cin][taps*Cout] bf16 (B operand of the 1x1 data-gradient GEMM)
+                packs[kind] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
             elif kind == 'convT_fwd':     # [Cin][taps*Cout] fp32
                 packs[kind] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).float().contiguous()
             elif kind == 'convT_dgrad':   # [taps*Cout][Cin] fp32
@@ -382,10 +386,19 @@ class UpConvCat(Function):
         call('ich_slab_copy', rp, rld, out.data_ptr(), ctot, _dt(x), m_out, cres, _stream())
         up = out[..., cres:]
         xp, xld = _rows(x)
-        call('ich_convT2_fwd', xp, xld, _p(_pack(weight, 'convT_fwd')), _p(bias), up.data_ptr(), ctot, _dt(x), n, d, h, w, cin, cout, fd,
-             _stream())
+        from ._lib import lib
+        use_tc = bool(config.get('tensor_cores') and x.dtype == torch.bfloat16 and cres % 8 == 0 and
+                      lib().ich_convT2_tc_supported(n, d, h, w, cin, cout, fd) and
+                      lib().ich_conv_tc_supported(n, d, h, w, 4 * fd * cout, cin, 1, 1, 1) and
+                      lib().ich_convT2_tc_wgrad_supported(n, d, h, w, cin, cout, fd))
+        if use_tc:
+            call('ich_convT2_tc_fwd', xp, xld, _p(_pack(weight, 'convT_fwd_tc')), _p(bias), up.data_ptr(), ctot, n, d, h, w, cin, cout, fd,
+                 _stream())
+        else:
+            call('ich_convT2_fwd', xp, xld, _p(_pack(weight, 'convT_fwd')), _p(bias), up.data_ptr(), ctot, _dt(x), n, d, h, w, cin, cout, fd,
+                 _stream())
         ctx.save_for_backward(x, weight)
-        ctx.fd, ctx.cres = fd, cres
+        ctx.fd, ctx.cres, ctx.use_tc = fd, cres, use_tc
         return out
 
     @staticmethod
@@ -404,6 +417,20 @@ class UpConvCat(Function):
             call('ich_slab_copy', dout.data_ptr(), ctot, dres.data_ptr(), cres, _dt(dout), m_out, cres, _stream())
         dup = dout[..., cres:]
         dx = dw = db = None
+        if ctx.use_tc and (need[0] or need[2]):
+            # re-pack the up-sampled gradient to the coarse grid once ([voxel][tap*Cout + co]); both gradients are then 1x1 GEMMs
+            taps = 4 * fd
+            g = torch.empty((n, d, h, w, taps * cout), dtype=dout.dtype, device=dout.device)
+            call('ich_space_to_depth2', dup.data_ptr(), ctot, g.data_ptr(), _dt(dout), n, d, h, w, cout, fd, _stream())
+            if need[0]:
+                dx = torch.empty_like(x)
+                call('ich_conv_tc_fwd', g.data_ptr(), taps * cout, _p(_pack(weight, 'convT_dgrad_tc')), None, dx.data_ptr(), cin, n, d, h, w,
+                     taps * cout, cin, 1, 1, 1, 0, _stream())
+            if need[2]:
+                dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+                xp, xld = _rows(x)
+                call('ich_convT2_tc_wgrad', xp, xld, g.data_ptr(), taps * cout, dw.data_ptr(), n, d, h, w, cin, cout, fd, _stream())
+            need = (False, need[1], False, need[3], need[4])
         if need[0]:
             dx = torch.empty_like(x)
             call('ich_convT2_dgrad', dup.data_ptr(), ctot, _p(_pack(weight, 'convT_dgrad')), dx.data_ptr(), cin, _dt(x), n, d, h, w, cin, cout,

@@ -123,9 +123,11 @@ def test_maxpool_with_ties(prec, fd):
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
 @pytest.mark.parametrize('fd', [2, 1])
-def test_upconv_cat(prec, fd):
+@pytest.mark.parametrize('chan', [(16, 8, 4, 4), (64, 32, 8, 16), (32, 16, 6, 128)])   # the wider ones run on tcgen05 in bf16 mode
+def test_upconv_cat(prec, fd, chan):
     g = torch.Generator().manual_seed(5)
-    n, cin, cout, d, h, w = 2, 16, 8, 2 if fd == 2 else 1, 4, 4
+    cin, cout, h, w = chan
+    n, d = 2, 2 if fd == 2 else 1
     x = torch.randn(n, cin, d, h, w, generator=g)
     res = torch.randn(n, cout, d * fd, h * 2, w * 2, generator=g)
     wt = torch.randn(cin, cout, fd, 2, 2, generator=g) * 0.3
