@@ -307,6 +307,154 @@ int launch_wgrad(const AOp& A, const GOp& G, const Out& out, Grid4 g, int Nn, in
   return ich_check_launch(what);
 }
 
+
+// ---- first layer (Cin == 1): bandwidth-bound direct kernels --------------------------------------------------------------
+// The network input has one channel (CT intensity): AI ~ 25 FLOP/B, so these are HBM / LSU bound, not tensor bound.
+// One block = one row segment (n, d, h, w0 .. w0+127); the KD*3 input rows it touches are staged (zero padded) in shared memory.
+constexpr int C1_SEG = 128;
+
+template <typename T, int COUT, int KD>
+__global__ void __launch_bounds__(C1_SEG) conv_cin1_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ wp /*[taps][COUT]*/,
+                                                               const float* __restrict__ bias, T* __restrict__ y, int y_ld, Grid4 g, int relu) {
+  constexpr int TAPS = KD * 9;
+  __shared__ float xs[KD * 3][C1_SEG + 2];
+  __shared__ __align__(16) float ws[TAPS][COUT];
+  const int nseg = (g.W + C1_SEG - 1) / C1_SEG;
+  const int seg = blockIdx.x % nseg;
+  long long row = blockIdx.x / nseg;               // (n*D + d)*H + h
+  const int h = (int)(row % g.H);
+  const long long r = row / g.H;                   // n*D + d
+  const int d = (int)(r % g.D);
+  const int w0 = seg * C1_SEG;
+  for (int i = threadIdx.x; i < TAPS * COUT; i += C1_SEG) ws[i / COUT][i % COUT] = wp[i];
+  for (int i = threadIdx.x; i < KD * 3 * (C1_SEG + 2); i += C1_SEG) {
+    const int rr = i / (C1_SEG + 2), pw = i - rr * (C1_SEG + 2);
+    const int kd = rr / 3, kh = rr - kd * 3;
+    const int dd = d + kd - KD / 2, hh = h + kh - 1, ww = w0 + pw - 1;
+    float v = 0.f;
+    if ((unsigned)dd < (unsigned)g.D && (unsigned)hh < (unsigned)g.H && (unsigned)ww < (unsigned)g.W)
+      v = to_f32(x[(((r - d + dd) * g.H + hh) * (long long)g.W + ww) * x_ld]);
+    xs[rr][pw] = v;
+  }
+  __syncthreads();
+  const int w = w0 + threadIdx.x;
+  if (w >= g.W) return;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int rr = 0; rr < KD * 3; ++rr)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const float xv = xs[rr][threadIdx.x + kw];
+#pragma unroll
+      for (int c = 0; c < COUT; c += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[rr * 3 + kw][c]);
+        acc[c] = fmaf(xv, wv.x, acc[c]); acc[c + 1] = fmaf(xv, wv.y, acc[c + 1]);
+        acc[c + 2] = fmaf(xv, wv.z, acc[c + 2]); acc[c + 3] = fmaf(xv, wv.w, acc[c + 3]);
+      }
+    }
+  if (relu)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = fmaxf(acc[c], 0.f);
+  T* out = y + (row * g.W + w) * y_ld;
+#pragma unroll
+  for (int c = 0; c < COUT; c += Vec<T>::N) Vec<T>::store(out + c, acc + c);
+}
+
+// dW[co][tap] = sum_vox dy[vox][co] * x[vox + tap].  Block = (co, w-slice) threads; per row the x rows and the dy row are staged in
+// shared memory; each thread slides a KD*3 x 3 register window along its w-slice.  Per-block partials -> fp32 atomics.
+template <typename T, int COUT, int KD>
+__global__ void __launch_bounds__(256) conv_cin1_wgrad_kernel(const T* __restrict__ x, int x_ld, const T* __restrict__ dy, int dy_ld,
+                                                              float* __restrict__ dw /*[COUT][taps]*/, Grid4 g, long long rows_total, int rows_per_block) {
+  constexpr int TAPS = KD * 9, ROWS = KD * 3, SLICES = 256 / COUT, WPS = C1_SEG / SLICES;   // w positions per slice
+  __shared__ float xs[ROWS][C1_SEG + 2];
+  __shared__ float ds[C1_SEG][COUT + 1];
+  const int co = threadIdx.x % COUT, sl = threadIdx.x / COUT;
+  const int nseg = (g.W + C1_SEG - 1) / C1_SEG;
+  float acc[TAPS];
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) acc[k] = 0.f;
+  const long long it0 = (long long)blockIdx.x * rows_per_block;
+  const long long it1 = min(rows_total * nseg, it0 + rows_per_block);
+  for (long long it = it0; it < it1; ++it) {
+    const int seg = (int)(it % nseg);
+    const long long row = it / nseg;
+    const int h = (int)(row % g.H);
+    const long long r = row / g.H;
+    const int d = (int)(r % g.D);
+    const int w0 = seg * C1_SEG;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ROWS * (C1_SEG + 2); i += 256) {
+      const int rr = i / (C1_SEG + 2), pw = i - rr * (C1_SEG + 2);
+      const int kd = rr / 3, kh = rr - kd * 3;
+      const int dd = d + kd - KD / 2, hh = h + kh - 1, ww = w0 + pw - 1;
+      float v = 0.f;
+      if ((unsigned)dd < (unsigned)g.D && (unsigned)hh < (unsigned)g.H && (unsigned)ww < (unsigned)g.W)
+        v = to_f32(x[(((r - d + dd) * g.H + hh) * (long long)g.W + ww) * x_ld]);
+      xs[rr][pw] = v;
+    }
+    for (int i = threadIdx.x; i < C1_SEG * COUT; i += 256) {
+      const int pw = i / COUT, c = i - pw * COUT;
+      const int ww = w0 + pw;
+      ds[pw][c] = ww < g.W ? to_f32(dy[(row * g.W + ww) * dy_ld + c]) : 0.f;
+    }
+    __syncthreads();
+    const int p0 = sl * WPS;
+    float win[ROWS][3];
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) { win[rr][1] = xs[rr][p0]; win[rr][2] = xs[rr][p0 + 1]; }
+#pragma unroll 4
+    for (int i = 0; i < WPS; ++i) {
+      const float a = ds[p0 + i][co];
+#pragma unroll
+      for (int rr = 0; rr < ROWS; ++rr) {
+        win[rr][0] = win[rr][1]; win[rr][1] = win[rr][2]; win[rr][2] = xs[rr][p0 + i + 2];
+        acc[rr * 3 + 0] = fmaf(a, win[rr][0], acc[rr * 3 + 0]);
+        acc[rr * 3 + 1] = fmaf(a, win[rr][1], acc[rr * 3 + 1]);
+        acc[rr * 3 + 2] = fmaf(a, win[rr][2], acc[rr * 3 + 2]);
+      }
+    }
+  }
+  // reduce the SLICES partials of each (co, tap) through shared memory, then one atomic per (co, tap) per block
+  __syncthreads();
+  float* red = &ds[0][0];     // >= COUT * TAPS floats: 128 * (COUT + 1) >= 27 * COUT
+  for (int i = threadIdx.x; i < COUT * TAPS; i += 256) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) atomicAdd(&red[co * TAPS + k], acc[k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * TAPS; i += 256) atomicAdd(&dw[i], red[i]);
+}
+
+template <typename T>
+bool cin1_fwd_launch(const T* x, int x_ld, const float* wp, const float* bias, T* y, int y_ld, Grid4 g, int Cout, int KD, int relu, cudaStream_t s) {
+  if (y_ld % Vec<T>::N || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
+  const int nseg = (g.W + C1_SEG - 1) / C1_SEG;
+  long long blocks = (long long)g.N * g.D * g.H * nseg;
+  if (blocks <= 0 || blocks > 0x7fffffffLL) return false;
+#define ICH_C1F(CO, K) conv_cin1_fwd_kernel<T, CO, K><<<(unsigned)blocks, C1_SEG, 0, s>>>(x, x_ld, wp, bias, y, y_ld, g, relu)
+  if (KD == 3) { if (Cout == 8) ICH_C1F(8, 3); else if (Cout == 16) ICH_C1F(16, 3); else if (Cout == 32) ICH_C1F(32, 3); else return false; }
+  else { if (Cout == 8) ICH_C1F(8, 1); else if (Cout == 16) ICH_C1F(16, 1); else if (Cout == 32) ICH_C1F(32, 1); else return false; }
+#undef ICH_C1F
+  return true;
+}
+
+template <typename T>
+bool cin1_wgrad_launch(const T* x, int x_ld, const T* dy, int dy_ld, float* dw, Grid4 g, int Cout, int KD, cudaStream_t s) {
+  const int nseg = (g.W + C1_SEG - 1) / C1_SEG;
+  long long rows = (long long)g.N * g.D * g.H, items = rows * nseg;
+  if (items <= 0) return false;
+  int rows_per_block = (int)((items + 8LL * ich_num_sms() - 1) / (8LL * ich_num_sms()));
+  if (rows_per_block < 1) rows_per_block = 1;
+  unsigned blocks = (unsigned)((items + rows_per_block - 1) / rows_per_block);
+#define ICH_C1W(CO, K) conv_cin1_wgrad_kernel<T, CO, K><<<blocks, 256, 0, s>>>(x, x_ld, dy, dy_ld, dw, g, rows, rows_per_block)
+  if (KD == 3) { if (Cout == 8) ICH_C1W(8, 3); else if (Cout == 16) ICH_C1W(16, 3); else if (Cout == 32) ICH_C1W(32, 3); else return false; }
+  else { if (Cout == 8) ICH_C1W(8, 1); else if (Cout == 16) ICH_C1W(16, 1); else if (Cout == 32) ICH_C1W(32, 1); else return false; }
+#undef ICH_C1W
+  return true;
+}
+
 }  // namespace
 
 // ---- C-ABI (declared in include/ich_b200.h) ---------------------------------------------------------------------
@@ -318,6 +466,11 @@ int ich_conv_fwd(const void* x, int x_ld, const float* wpack, const float* bias,
   cudaStream_t s = (cudaStream_t)stream;
   int Ktot = KD * KH * KW * Cin;
   ICH_REQUIRE((KD & 1) && (KH & 1) && (KW & 1), "ich_conv_fwd: odd kernel sizes only (got %dx%dx%d)", KD, KH, KW);
+  if (Cin == 1 && KH == 3 && KW == 3 && (KD == 1 || KD == 3)) {   // first layer: direct bandwidth-bound kernel
+    bool done = dtype == ICH_F32 ? cin1_fwd_launch<float>((const float*)x, x_ld, wpack, bias, (float*)y, y_ld, g, Cout, KD, relu, s)
+              : dtype == ICH_BF16 ? cin1_fwd_launch<bf16>((const bf16*)x, x_ld, wpack, bias, (bf16*)y, y_ld, g, Cout, KD, relu, s) : false;
+    if (done) return ich_check_launch("ich_conv_fwd<cin1>");
+  }
   if (dtype == ICH_F32) {
     AConv<float> A{(const float*)x, x_ld, Cin, KD, KH, KW, g};
     EpiRow<float> E{(float*)y, y_ld, bias, relu};
@@ -336,6 +489,11 @@ int ich_conv_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, int dtype
   cudaStream_t s = (cudaStream_t)stream;
   int taps = KD * KH * KW, Ktot = taps * Cin;
   if (cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Ktot, s) != cudaSuccess) return ich_check_launch("ich_conv_wgrad memset");
+  if (Cin == 1 && KH == 3 && KW == 3 && (KD == 1 || KD == 3)) {   // first layer: dW[co][0][tap] == [Cout][taps]
+    bool done = dtype == ICH_F32 ? cin1_wgrad_launch<float>((const float*)x, x_ld, (const float*)dy, dy_ld, dw, g, Cout, KD, s)
+              : dtype == ICH_BF16 ? cin1_wgrad_launch<bf16>((const bf16*)x, x_ld, (const bf16*)dy, dy_ld, dw, g, Cout, KD, s) : false;
+    if (done) return ich_check_launch("ich_conv_wgrad<cin1>");
+  }
   OutConvW O{dw, Cin, taps};
   if (dtype == ICH_F32) {
     AConv<float> A{(const float*)x, x_ld, Cin, KD, KH, KW, g};

@@ -31,6 +31,7 @@ def nc(x):                 # channel-last cuda -> NCDHW cpu fp32
 CONV_CASES = [  # N, D, H, W, Cin, Cout, k3d
     (2, 4, 8, 8, 1, 8, True), (1, 3, 5, 7, 3, 5, True), (2, 4, 8, 16, 16, 32, True), (1, 2, 4, 4, 64, 32, True),
     (2, 1, 16, 16, 8, 16, False), (1, 1, 9, 11, 4, 6, False), (1, 8, 16, 16, 32, 32, True),
+    (1, 1, 16, 24, 1, 16, False), (1, 3, 6, 140, 1, 32, True), (2, 2, 5, 16, 1, 16, True),      # first-layer (Cin = 1) direct kernels
 ]
 
 
