@@ -529,6 +529,7 @@ struct WParams {
   long long n_pos_items;   // N * D * n_rb * n_wb
   int splits;
   float* dw;
+  int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA loads
 };
 
 template <int KS>
@@ -572,7 +573,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
         uint8_t* sb = sa + p.a_bytes;
-        if (elect_one()) {
+        if (p.dbg & 2) { if (elect_one()) mbar_arrive(&full_bar[stage]); }
+        else if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
           for (int pl = 0; pl < p.KD; ++pl) {
             const int dd = d + pl - (p.KD == 3 ? 1 : 0);
@@ -601,7 +603,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
         uint32_t a_row = ((sa & 0x3FFFFu) >> 4) | (8u << 16);                      // one position = 16 B = 1 unit
         uint32_t b_row = (((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (8u << 16);
-        for (int r = 0; r < p.R; ++r, a_row += PW, b_row += WB) {
+        for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, b_row += WB) {
           for (uint32_t s16 = 0; s16 < WB; s16 += 16) {
             const uint64_t bdesc = pack64(b_row + s16, b_hi);
             uint32_t a_kh = a_row + s16;
@@ -744,6 +746,7 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
   EncodeTiledFn enc = get_encode();
   ICH_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled not available", what);
   p.dw = dw;
+  { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (cudaMemsetAsync(dw, 0, sizeof(float) * dw_elems, s) != cudaSuccess) return ich_check_launch(what);
 
   CUtensorMap map_x, map_dy;

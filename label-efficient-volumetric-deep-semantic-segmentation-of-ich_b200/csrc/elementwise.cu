@@ -284,6 +284,145 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   }
 }
 
+
+// ---- fast paths: C/V divides 256, so a thread owns ONE 16-byte channel group for the whole kernel (per-channel constants live
+//      in registers, no index division in the loop) and strides over rows with several independent loads in flight. ---------
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, T* __restrict__ z, int z_ld, long long M, int C, int relu) {
+  constexpr int V = Vec<T>::N;
+  const int groups = C / V, rpb = 256 / groups;
+  const int c = (threadIdx.x % groups) * V;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { sc[k] = scale[c + k]; sh[k] = shift[c + k]; }
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
+  for (; r + step < M; r += 2 * step) {
+    float a[V], b[V];
+    Vec<T>::load(y + r * y_ld + c, a);
+    Vec<T>::load(y + (r + step) * y_ld + c, b);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      a[k] = fmaf(a[k], sc[k], sh[k]); b[k] = fmaf(b[k], sc[k], sh[k]);
+      if (relu) { a[k] = fmaxf(a[k], 0.f); b[k] = fmaxf(b[k], 0.f); }
+    }
+    Vec<T>::store(z + r * z_ld + c, a);
+    Vec<T>::store(z + (r + step) * z_ld + c, b);
+  }
+  if (r < M) {
+    float a[V];
+    Vec<T>::load(y + r * y_ld + c, a);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { a[k] = fmaf(a[k], sc[k], sh[k]); if (relu) a[k] = fmaxf(a[k], 0.f); }
+    Vec<T>::store(z + r * z_ld + c, a);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean, const float* __restrict__ invstd, long long M, int C,
+                                                                 int relu, double* __restrict__ sums) {
+  constexpr int V = Vec<T>::N;
+  const int groups = C / V, rpb = 256 / groups;
+  const int c = (threadIdx.x % groups) * V;
+  float sc[V], sf[V], mu[V], is[V], sb[V], sg[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { sc[k] = scale[c + k]; sf[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; sb[k] = sg[k] = 0.f; }
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
+  for (; r + step < M; r += 2 * step) {
+    float a0[V], b0[V], a1[V], b1[V];
+    Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
+    Vec<T>::load(dz + (r + step) * dz_ld + c, a1); Vec<T>::load(y + (r + step) * y_ld + c, b1);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
+      float g1 = (!relu || fmaf(b1[k], sc[k], sf[k]) > 0.f) ? a1[k] : 0.f;
+      sb[k] += g0 + g1;
+      sg[k] = fmaf(g0, (b0[k] - mu[k]) * is[k], sg[k]);
+      sg[k] = fmaf(g1, (b1[k] - mu[k]) * is[k], sg[k]);
+    }
+  }
+  if (r < M) {
+    float a0[V], b0[V];
+    Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
+      sb[k] += g0;
+      sg[k] = fmaf(g0, (b0[k] - mu[k]) * is[k], sg[k]);
+    }
+  }
+  extern __shared__ float sh[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < V; ++k) { atomicAdd(&sh[c + k], sb[k]); atomicAdd(&sh[C + c + k], sg[k]); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const double* __restrict__ sums, T* __restrict__ dy, int dy_ld, long long M, int C,
+                                                                int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int V = Vec<T>::N;
+  const int groups = C / V, rpb = 256 / groups;
+  const int c = (threadIdx.x % groups) * V;
+  const float invM = training ? (float)(1.0 / (double)M) : 0.f;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      if (dbeta) dbeta[i] = (float)sums[i];
+      if (dgamma) dgamma[i] = (float)sums[C + i];
+    }
+  // dy = sc * g - k0 - y * k1  with  k1 = sc * is * dgamma/M,  k0 = sc * dbeta/M - mu * k1
+  float sc[V], sf[V], k0[V], k1[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    sc[k] = scale[c + k]; sf[k] = shift[c + k];
+    k1[k] = sc[k] * invstd[c + k] * (float)sums[C + c + k] * invM;
+    k0[k] = sc[k] * (float)sums[c + k] * invM - mean[c + k] * k1[k];
+  }
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
+  for (; r + step < M; r += 2 * step) {
+    float a0[V], b0[V], a1[V], b1[V];
+    Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
+    Vec<T>::load(dz + (r + step) * dz_ld + c, a1); Vec<T>::load(y + (r + step) * y_ld + c, b1);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
+      float g1 = (!relu || fmaf(b1[k], sc[k], sf[k]) > 0.f) ? a1[k] : 0.f;
+      a0[k] = fmaf(sc[k], g0, -fmaf(b0[k], k1[k], k0[k]));
+      a1[k] = fmaf(sc[k], g1, -fmaf(b1[k], k1[k], k0[k]));
+    }
+    Vec<T>::store(dy + r * dy_ld + c, a0);
+    Vec<T>::store(dy + (r + step) * dy_ld + c, a1);
+  }
+  if (r < M) {
+    float a0[V], b0[V];
+    Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
+      a0[k] = fmaf(sc[k], g0, -fmaf(b0[k], k1[k], k0[k]));
+    }
+    Vec<T>::store(dy + r * dy_ld + c, a0);
+  }
+}
+
+inline bool rows_fast_ok(int C, int V) { return C % V == 0 && (C / V) <= 256 && 256 % (C / V) == 0; }
+inline int rows_grid(long long M, int C, int V) {
+  const int rpb = 256 / (C / V);
+  long long blocks = (M + rpb - 1) / rpb;
+  long long cap = (long long)ich_num_sms() * 8;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
 // ---- 2x max-pool (kernel 2 stride 2; depth factor FD = 2 or 1) ------------------------------------------------------
 // Tie rule = ATen max_pool3d_with_indices: scan (d,h,w) in order, update on strict '>' (NaN propagates) -> first max wins.
 template <typename T, bool VEC>
@@ -473,7 +612,9 @@ int ich_affine_act(const void* y, int y_ld, const float* scale, const float* shi
   cudaStream_t s = (cudaStream_t)stream;
   if (M * C == 0) return 0;
   DISPATCH_T(dtype, "ich_affine_act", {
-    if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C))
+    if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C) && rows_fast_ok(C, Vec<T>::N))
+      affine_act_rows_kernel<T><<<rows_grid(M, C, Vec<T>::N), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
+    else if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C))
       affine_act_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
     else
       affine_act_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
@@ -492,7 +633,11 @@ int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const flo
   size_t shbytes = sizeof(float) * 2 * C;
   DISPATCH_T(dtype, "ich_bn_act_bwd", {
     bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
-    if (vec) {
+    if (vec && rows_fast_ok(C, Vec<T>::N)) {
+      const int grid = rows_grid(M, C, Vec<T>::N);
+      bn_bwd_reduce_rows_kernel<T><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums);
+      bn_bwd_apply_rows_kernel<T><<<grid, 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta);
+    } else if (vec) {
       bn_bwd_reduce_kernel<T, true><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block);
       bn_bwd_apply_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta);
     } else {
