@@ -674,12 +674,8 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
   if (N <= 0 || D <= 0 || H <= 0) return pl;
-  int WB;
-  if (W <= 128) WB = W;
-  else if (W % 128 == 0) WB = 128;
-  else return pl;
-  if (WB % 16) return pl;
-  const int PW = WB + 2 * hw;
+  if (W > 128 && W % 128) return pl;
+  if (W % 16) return pl;
   int CU = 0;
   const int cu_max = KD == 3 ? 32 : 128;
   for (int c = cu_max; c >= 16; c -= 16)
@@ -689,20 +685,27 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
     if (Cout % c == 0) { NB = c; break; }
   if (!CU || !NB) return pl;
   const int chunks_u = CU / 8, chunks_v = NB / 8;
-  int bestR = 0;
+  // Search the slab shape (w-block WB x R rows): the full-resolution layers are bound by L2->SMEM traffic, so minimise the halo
+  // amplification (RB/R)*(PW/WB) of the x slab under the shared-memory budget (narrower w-blocks allow more rows per slab).
+  int bestR = 0, WB = 0, PW = 0;
   size_t best_smem = 0;
-  for (int R = 1; R <= H + 1 && R <= 32; ++R) {
-    const int RB = R + 2 * hw;
-    if ((chunks_u * RB) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
-    size_t a = (size_t)KD * chunks_u * RB * PW * 16;
-    size_t b = (size_t)chunks_v * R * WB * 16;
-    size_t stage = (a + b + 1023) & ~(size_t)1023;
-    // the MMA always reads 16 chunks (128 rows): chunks beyond KD*chunks_u are garbage rows, but must stay inside the allocation
-    size_t over = (size_t)(16 - KD * chunks_u > 0 ? 16 - KD * chunks_u : 0) * RB * PW * 16 + (size_t)(2 * PW + 32) * 16;
-    size_t total = STAGES * stage + over + 1024;
-    if (total > SMEM_LIMIT) break;
-    bestR = R;
-    best_smem = total;
+  double best_amp = 1e30;
+  for (int wb = (W <= 128 ? W : 128); wb >= 16; wb >>= 1) {
+    if (wb % 16 || W % wb) continue;
+    const int pw = wb + 2 * hw;
+    for (int R = 1; R <= H + 1 && R <= 32; ++R) {
+      const int RB = R + 2 * hw;
+      if ((chunks_u * RB) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
+      size_t a = (size_t)KD * chunks_u * RB * pw * 16;
+      size_t b = (size_t)chunks_v * R * wb * 16;
+      size_t stage = (a + b + 1023) & ~(size_t)1023;
+      // the MMA always reads 16 chunks (128 rows): chunks beyond KD*chunks_u are garbage rows, but must stay inside the allocation
+      size_t over = (size_t)(16 - KD * chunks_u > 0 ? 16 - KD * chunks_u : 0) * RB * pw * 16 + (size_t)(2 * pw + 32) * 16;
+      size_t total = STAGES * stage + over + 1024;
+      if (total > SMEM_LIMIT) break;
+      const double amp = ((double)RB / R) * ((double)pw / wb) * (1.0 + 0.02 * (128 / wb)) * (1.0 + 0.05 / R);   // mild preference for wide blocks / more rows
+      if (amp < best_amp) { best_amp = amp; bestR = R; WB = wb; PW = pw; best_smem = total; }
+    }
   }
   if (!bestR) return pl;
   WParams& p = pl.p;
