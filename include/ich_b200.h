@@ -44,6 +44,9 @@ int ich_conv_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, int dtype
 int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
 int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
                     int Cin, int Cout, int KD, int KH, int KW, int relu, void* stream);
+/* same, with the BatchNorm batch statistics (fp64 per-channel sum / sum of squares of the stored outputs) fused into the epilogue */
+int ich_conv_tc_fwd_stats(const void* x, int x_ld, const void* wpack_bf16, void* y, int y_ld, double* sum, double* sumsq, int N, int D,
+                          int H, int W, int Cin, int Cout, int KD, int KH, int KW, void* stream);
 /* transposed conv k2 s2 on tensor cores (same call site as ich_convT2_fwd): 1x1 GEMM + depth-to-space scatter epilogue.
  * wpack_bf16 = [taps*Cout][Cin] bf16.  Grid args = the COARSE grid.                                                   */
 int ich_convT2_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int FD);

@@ -152,13 +152,15 @@ struct Params {
   int y_ld;
   const float* bias;
   int relu;
+  double* stat_sum;     // optional fused BatchNorm statistics (per output channel sum / sum of squares of the stored bf16 values)
+  double* stat_sumsq;
   int dbg;   // ablation switches for profiling only (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue stores
 };
 
 constexpr int STAGES = 2;
 constexpr int NUM_THREADS = 192;
 
-template <int KS>
+template <int KS, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -184,14 +186,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   const uint32_t tmem_base = tmem_base_smem;
 
   const int planes_lo = (p.KD == 3) ? 1 : 0;     // slab plane 0 corresponds to d - planes_lo
+  // a CTA keeps ONE cout block for its whole life (per-thread BatchNorm partial sums stay valid); CTAs that share a
+  // spatial item (same slab, different cout block) are neighbours -> the slab is served from L2 for the second one
+  const int nb_fixed = (int)(blockIdx.x % p.n_nb);
+  const long long s_begin = blockIdx.x / p.n_nb, s_step = gridDim.x / p.n_nb, n_spatial = p.n_items / p.n_nb;
 
   if (warp == 0) {
     // ===================================================== TMA producer (warp-uniform loop, elected lane issues)
     {
       int stage = 0; uint32_t phase = 0;
-      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        long long t = item;
-        const int nb = (int)(t % p.n_nb); t /= p.n_nb;
+      for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
+        long long t = sp;
+        const int nb = nb_fixed;
         const int wb = (int)(t % p.n_wb); t /= p.n_wb;
         const int rb = (int)(t % p.n_rb); t /= p.n_rb;
         const int d = (int)(t % p.D); const int n = (int)(t / p.D);
@@ -228,8 +234,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const int T = p.T;
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;
-      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        long long t = item / p.n_nb / p.n_wb / p.n_rb;
+      for (long long sp = s_begin; sp < n_spatial; sp += s_step, ++it) {
+        long long t = sp / p.n_wb / p.n_rb;
         const int d = (int)(t % p.D);
         const int kd_lo = (p.KD == 3 && d == 0) ? 1 : 0;
         const int kd_hi = (p.KD == 3) ? ((d == p.D - 1) ? 1 : 2) : 0;
@@ -279,9 +285,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int q = warp & 3;
     const int l = q * 32 + lane;
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      long long t = item;
-      const int nb = (int)(t % p.n_nb); t /= p.n_nb;
+    float csum[STATS ? 64 : 1], csq[STATS ? 64 : 1];
+    if (STATS) {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) csum[k] = csq[k] = 0.f;
+    }
+    for (long long sp = s_begin; sp < n_spatial; sp += s_step, ++it) {
+      long long t = sp;
+      const int nb = nb_fixed;
       const int wb = (int)(t % p.n_wb); t /= p.n_wb;
       const int rb = (int)(t % p.n_rb); t /= p.n_rb;
       const int d = (int)(t % p.D); const int n = (int)(t / p.D);
@@ -306,27 +317,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
         bf16* yrow = p.y + vox * p.y_ld + bias0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
-        for (int c0 = 0; c0 < p.NB; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)c0, v);
-          tmem_ld_wait();
-          if (valid && !(p.dbg & 4)) {
-            float f32[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              float a = __uint_as_float(v[k]);
-              if (p.bias) a += p.bias[bias0 + c0 + k];
-              if (p.relu) a = fmaxf(a, 0.f);
-              f32[k] = a;
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          if (c0 < p.NB) {
+            uint32_t v[16];
+            tmem_ld16(taddr + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (valid && !(p.dbg & 4)) {
+              float f32[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                float a = __uint_as_float(v[k]);
+                if (p.bias) a += p.bias[bias0 + c0 + k];
+                if (p.relu) a = fmaxf(a, 0.f);
+                f32[k] = a;
+                if (STATS) {   // statistics of the value as stored (bf16-rounded)
+                  const float rv = __bfloat162float(__float2bfloat16_rn(a));
+                  csum[c0 + k] += rv;
+                  csq[c0 + k] = fmaf(rv, rv, csq[c0 + k]);
+                }
+              }
+              Vec<bf16>::store(yrow + c0, f32);
+              Vec<bf16>::store(yrow + c0 + 8, f32 + 8);
             }
-            Vec<bf16>::store(yrow + c0, f32);
-            Vec<bf16>::store(yrow + c0 + 8, f32 + 8);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if (STATS) {   // once per CTA: warp tree over the 32 voxel lanes, then one fp64 atomic per channel per warp
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        if (k < p.NB) {
+          const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
+          if (lane == 0) {
+            atomicAdd(&p.stat_sum[nb_fixed * p.NB + k], (double)a);
+            atomicAdd(&p.stat_sumsq[nb_fixed * p.NB + k], (double)b);
+          }
+        }
+      }
     }
   }
 
@@ -434,7 +465,7 @@ int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD,
 }
 
 static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int relu,
-                          cudaStream_t stream, const char* what) {
+                          cudaStream_t stream, const char* what, double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
   Params& p = pl.p;
   const int N = p.N, D = p.D, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout, KD = p.KD;
   ICH_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wpack_bf16 & 15) == 0,
@@ -442,7 +473,13 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   EncodeTiledFn enc = get_encode();
   ICH_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled not available", what);
   p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
+  p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
   { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  if (stat_sum) {
+    ICH_REQUIRE(stat_sumsq != nullptr && p.KS == 3 && !p.up_fd, "%s: fused statistics need both buffers and a 3x3 conv", what);
+    cudaMemsetAsync(stat_sum, 0, sizeof(double) * Cout, stream);
+    cudaMemsetAsync(stat_sumsq, 0, sizeof(double) * Cout, stream);
+  }
 
   CUtensorMap map_x, map_w;
   {
@@ -468,15 +505,19 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e != cudaSuccess) cudaGetLastError();
     ICH_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr_set = true;
   }
   long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
-  if (p.KS == 3) conv_tc_kernel<3><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else conv_tc_kernel<1><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  grid = grid / p.n_nb * p.n_nb;             // every CTA owns one cout block; n_items is a multiple of n_nb
+  if (grid < p.n_nb) grid = p.n_nb;
+  if (p.KS == 3 && stat_sum) conv_tc_kernel<3, true><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else if (p.KS == 3) conv_tc_kernel<3, false><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else conv_tc_kernel<1, false><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
   return ich_check_launch(what);
 }
 
@@ -485,6 +526,15 @@ int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float
   Plan pl = make_plan(N, D, H, W, Cin, Cout, KD, KH, KW);
   ICH_REQUIRE(pl.ok, "ich_conv_tc_fwd: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
   return launch_conv_tc(pl, x, x_ld, wpack_bf16, bias, y, y_ld, relu, (cudaStream_t)stream, "ich_conv_tc_fwd");
+}
+
+// Forward conv with the BatchNorm batch statistics fused into the epilogue: sum[c], sumsq[c] (fp64, zeroed here) of the stored
+// bf16 outputs -- replaces the separate ich_colstats pass over y.
+int ich_conv_tc_fwd_stats(const void* x, int x_ld, const void* wpack_bf16, void* y, int y_ld, double* sum, double* sumsq, int N, int D, int H,
+                          int W, int Cin, int Cout, int KD, int KH, int KW, void* stream) {
+  Plan pl = make_plan(N, D, H, W, Cin, Cout, KD, KH, KW);
+  ICH_REQUIRE(pl.ok && KH == 3, "ich_conv_tc_fwd_stats: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
+  return launch_conv_tc(pl, x, x_ld, wpack_bf16, nullptr, y, y_ld, 0, (cudaStream_t)stream, "ich_conv_tc_fwd_stats", sum, sumsq);
 }
 
 // Transposed conv k2 s2 on tensor cores: a 1x1 GEMM [voxels x Cin] x [Cin x taps*Cout] whose epilogue scatters every

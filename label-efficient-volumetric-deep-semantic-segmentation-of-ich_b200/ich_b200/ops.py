@@ -268,11 +268,20 @@ class ConvBnRelu(Function):
         m = n * d * h * w
         dev = x.device
         # training: BatchNorm cancels the conv bias, so the kernel skips it and bn_finalize folds it into running_mean
-        y = conv_forward(x, weight, None)
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)      # scale, shift, mean, invstd
         sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
-        if training:
-            call('ich_colstats', y.data_ptr(), cout, _dt(y), m, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+        k = _ksize(weight)
+        if training and k[1] == 3 and _use_tc(x, cin, cout, k):
+            # tcgen05 conv with the batch statistics accumulated in its epilogue (no separate pass over y)
+            y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=dev)
+            xp, xld = _rows(x)
+            with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
+                call('ich_conv_tc_fwd_stats', xp, xld, _p(_pack(weight, 'conv_fwd_tc')), y.data_ptr(), cout, sums[0].data_ptr(),
+                     sums[1].data_ptr(), n, d, h, w, cin, cout, *k, _stream())
+        else:
+            y = conv_forward(x, weight, None)
+            if training:
+                call('ich_colstats', y.data_ptr(), cout, _dt(y), m, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
         call('ich_bn_finalize', sums[0].data_ptr(), sums[1].data_ptr(), m, cout, _p(gamma), _p(beta), _p(bias), _p(running_mean),
              _p(running_var), BN_MOMENTUM, BN_EPS, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
              int(training), _stream())

@@ -63,9 +63,11 @@ def test_conv_fwd_dgrad_wgrad(case, prec):
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
 @pytest.mark.parametrize('training', [True, False])
-def test_conv_bn_relu_unit(prec, training):
+@pytest.mark.parametrize('chan', [(8, 16), (16, 32), (32, 128)])   # the last two run the tcgen05 conv with fused BN statistics in bf16 mode
+def test_conv_bn_relu_unit(prec, training, chan):
     g = torch.Generator().manual_seed(3)
-    n, cin, cout, d, h, w = 2, 8, 16, 8, 16, 16     # 4096 voxels per channel: single ReLU-mask flips stay well inside the tolerance
+    cin, cout = chan
+    n, d, h, w = 2, 8, 16, 16     # 4096 voxels per channel: single ReLU-mask flips stay well inside the tolerance
     x = torch.randn(n, cin, d, h, w, generator=g)
     conv = torch.nn.Conv3d(cin, cout, 3, padding=1)
     bn = torch.nn.BatchNorm3d(cout)
