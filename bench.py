@@ -94,7 +94,7 @@ def cpu_reference_step(sample_shape, threads, max_seconds=25.0, steps=3, warmup=
     return x.numel() / best, best, len(times)
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -132,10 +132,16 @@ def run_reference(args):
             'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'reference_sample': sample},
             'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: route everything else written to fd 1 (NCCL banners, library chatter) to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -146,7 +152,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -207,7 +213,6 @@ def main():
     l0 = _lib.launches()
     t_dev = timed(lambda: step(xd, md), args.steps)
     launches = _lib.launches() - l0
-    sampler.stop_flag = True
 
     # dominant kernel (implicit-GEMM conv fwd / dgrad / wgrad): CUDA events around every launch over a second timed pass
     ops.PROFILE = []
@@ -224,14 +229,16 @@ def main():
     peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
     achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
-    # end to end through the public API with host (pinned) inputs and a host read of the loss every step
-    def e2e_step():
-        x = xh.to(dev, non_blocking=True)
-        m = mh.to(dev, non_blocking=True)
-        return step(x, m).item()
-    for _ in range(2):
-        e2e_step()
-    t_e2e = timed(e2e_step, args.steps)
+    # end to end through the public API: every step's inputs come from pinned HOST memory (copied inside the timed region,
+    # one batch of look-ahead on a side stream = ich_b200.staging.DevicePrefetcher) and the loss is read back to the host
+    from ich_b200.staging import DevicePrefetcher
+
+    def e2e_run(steps):
+        for x, m in DevicePrefetcher([(xh, mh)] * steps, dev):
+            step(x, m).item()
+    e2e_run(2)
+    t_e2e = timed(lambda: e2e_run(args.steps), 1)
+    sampler.stop_flag = True
     sampler.join(timeout=2)
 
     cpu = None
@@ -261,7 +268,7 @@ def main():
         }
         if cpu:
             line['cpu_baseline'] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -772,7 +772,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   p.tmem_cols = cols;
   p.n_pos_items = (long long)N * D * p.n_rb * p.n_wb;
   const int pairs = p.n_cb * p.n_nb;
-  long long splits = (ich_num_sms() + pairs - 1) / pairs;
+  long long splits = ich_num_sms() / pairs;      // ONE wave: splits * pairs <= #SMs (a partial second wave would double the time)
   if (splits > p.n_pos_items) splits = p.n_pos_items;
   if (splits < 1) splits = 1;
   p.splits = (int)splits;

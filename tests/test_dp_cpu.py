@@ -123,3 +123,20 @@ def test_sliding_window_matches_oracle_rule_single_process():
         got, gm = infer.sliding_window_predict(OracleNet(), vol, window, stride, batch=3, distributed=False)
         want, wm = UO.sliding_window_predict(vol, sd, window, stride)
         assert torch.allclose(got, want, atol=1e-6) and torch.equal(gm, wm)
+
+
+def test_prefetcher_and_window_ct_host_logic():
+    """DevicePrefetcher yields every batch once, in order, with nested structures intact (CPU device = passthrough);
+    window_ct matches the reference formula (utils/ct_utils.py:13-36)."""
+    import numpy as np
+    from ich_b200.staging import DevicePrefetcher, window_ct
+    batches = [(torch.full((2, 1, 4, 4), float(i)), torch.zeros(2, 1, 4, 4, dtype=torch.bool), torch.tensor([i, i]), {'k': torch.tensor(i)})
+               for i in range(5)]
+    got = list(DevicePrefetcher(batches, 'cpu'))
+    assert len(got) == 5 and all(torch.equal(g[0], b[0]) and g[3]['k'].item() == i for i, (g, b) in enumerate(zip(got, batches)))
+    assert list(DevicePrefetcher([], 'cpu')) == []
+    hu = torch.tensor([-1000.0, -20.0, 40.0, 100.0, 3000.0])
+    ref = (hu.numpy() - (40 - 60)) / 120.0
+    ref = np.clip(ref, 0, 1)
+    assert np.allclose(window_ct(hu).numpy(), ref)
+    assert np.allclose(window_ct(hu, 50, 100, (0, 255)).numpy(), np.clip(255 * (hu.numpy() - 0) / 100.0, 0, 255))
