@@ -20,28 +20,52 @@ def _map(obj, fn):
 
 
 class DevicePrefetcher:
-    """for batch in DevicePrefetcher(loader, device): ...   (one batch of look-ahead, pinned staging, side stream)."""
+    """for batch in DevicePrefetcher(loader, device): ...
+
+    One batch of look-ahead: batch k+1 is copied host->device on a side stream while step k runs.  Device buffers are
+    three static sets per (shape, dtype) slot used round-robin (no allocator traffic in the loop), so a yielded batch stays
+    valid until two further batches have been requested."""
+
+    SETS = 3
 
     def __init__(self, loader, device):
         self.loader = loader
         self.device = torch.device(device)
         self.cuda = self.device.type == 'cuda'
         self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self._bufs = {}
+        self._turn = 0
 
     def __len__(self):
         return len(self.loader)
 
+    def _buffer(self, slot, t):
+        key = (slot, self._turn % self.SETS, tuple(t.shape), t.dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            b = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+            self._bufs[key] = b
+        return b
+
     def _stage(self, batch):
         if not self.cuda:
             return batch
+        # the buffer set being overwritten was handed out SETS batches ago; order the copy after the compute stream's work
+        # enqueued so far (which includes every kernel that read it), then overlap with the step launched next
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        slot = [0]
         with torch.cuda.stream(self.stream):
             def put(t):
                 if t.is_cuda:
                     return t
+                i = slot[0]
+                slot[0] += 1
                 if not t.is_pinned():
                     t = t.pin_memory()
-                return t.to(self.device, non_blocking=True)
-            return _map(batch, put)
+                return self._buffer(i, t).copy_(t, non_blocking=True)
+            out = _map(batch, put)
+        self._turn += 1
+        return out
 
     def __iter__(self):
         it = iter(self.loader)
@@ -53,7 +77,6 @@ class DevicePrefetcher:
             cur = nxt
             if self.cuda:
                 torch.cuda.current_stream(self.device).wait_stream(self.stream)
-                _map(cur, lambda t: t.record_stream(torch.cuda.current_stream(self.device)) if t.is_cuda else None)
             try:
                 nxt = self._stage(next(it))
             except StopIteration:
