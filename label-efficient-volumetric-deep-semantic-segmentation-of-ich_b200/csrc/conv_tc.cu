@@ -145,7 +145,7 @@ struct Params {
   int WB, PW, R, RB, T, row_mode, NB;
   int up_fd, up_cout;                  // transposed-conv scatter epilogue: depth factor (0 = off) and its Cout
   int n_wb, n_rb, n_nb, KC, taps;
-  int nacc;
+  int nacc, stages;
   uint32_t a_bytes, a_tx_bytes, b_bytes, stage_bytes, tmem_cols;
   long long n_items;
   bf16* y;
@@ -157,7 +157,8 @@ struct Params {
   int dbg;   // ablation switches for profiling only (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue stores
 };
 
-constexpr int STAGES = 2;
+constexpr int STAGES = 2;        // weight-gradient kernel
+constexpr int MAX_STAGES = 8;    // forward kernel: runtime depth (2 for the big 3x3 slabs, up to 8 for the small 1x1 GEMM stages)
 constexpr int NUM_THREADS = 192;
 
 template <int KS, bool STATS>
@@ -166,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage0 A|B][stage1 A|B] ... then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   // broadcast from lane 0 so the compiler KNOWS the role index is warp-uniform (uniform branches + uniform datapath)
@@ -175,7 +176,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
     fence_barrier_init();
   }
@@ -215,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -274,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           }
           __syncwarp();
           if (elect_one()) umma_commit(&empty_bar[stage]);            // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) umma_commit(&tfull_bar[acc]);                // accumulators complete
         __syncwarp();
@@ -318,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         bf16* yrow = p.y + vox * p.y_ld + bias0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int c0 = 0; c0 < (KS == 1 ? 256 : 64); c0 += 16) {
           if (c0 < p.NB) {
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
@@ -331,10 +332,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (p.bias) a += p.bias[bias0 + c0 + k];
                 if (p.relu) a = fmaxf(a, 0.f);
                 f32[k] = a;
-                if (STATS) {   // statistics of the value as stored (bf16-rounded)
+                if (STATS && c0 < 64) {   // statistics of the value as stored (bf16-rounded)
                   const float rv = __bfloat162float(__float2bfloat16_rn(a));
-                  csum[c0 + k] += rv;
-                  csq[c0 + k] = fmaf(rv, rv, csq[c0 + k]);
+                  csum[(c0 + k) & 63] += rv;
+                  csq[(c0 + k) & 63] = fmaf(rv, rv, csq[(c0 + k) & 63]);
                 }
               }
               Vec<bf16>::store(yrow + c0, f32);
@@ -404,44 +405,54 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   else if (W % 128 == 0) WB = 128;
   else return pl;
   const int PW = WB + 2 * hw;
-  int NB = 0;
-  for (int c = 64; c >= 16; c -= 16)
-    if (Cout % c == 0 && (!nb_must_divide || nb_must_divide % c == 0)) { NB = c; break; }
-  if (!NB) return pl;
   const int taps = KD * KS * KS;
-  const uint32_t b_bytes = (uint32_t)taps * 2u * NB * 16u;
   const bool row_mode = (WB == 128);
   long long best_cost = -1;
-  int bestR = 0, bestT = 0, bestAcc = 0;
+  int bestR = 0, bestT = 0, bestAcc = 0, bestNB = 0, bestStages = 0;
   size_t best_smem = 0;
   uint32_t best_a = 0;
-  for (int R = 1; R <= H && R <= 64; ++R) {
-    const int RB = R + 2 * hw;
-    const int T = row_mode ? R : (((R - 1) * PW + WB) + 127) / 128;
-    int nacc = 0;
-    if (2 * T * NB <= 512) nacc = 2;
-    else if (T * NB <= 512) nacc = 1;
-    else continue;
-    uint32_t a_bytes = (uint32_t)KD * 2u * RB * PW * 16u;
-    a_bytes = (a_bytes + 127u) & ~127u;
-    long long over = row_mode ? 0 : ((long long)(128 * T + 2 * hw * PW + 2 * hw) - (long long)RB * PW) * 32;
-    if (over < 0) over = 0;
-    size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
-    size_t total = STAGES * stage + (size_t)over + 1024;   // +1024: manual alignment of the dynamic base
-    if (total > SMEM_LIMIT) continue;
-    long long blocks = (H + R - 1) / R;
-    long long cost = blocks * T * 1000 + blocks * RB * 20 + (nacc == 1 ? blocks * T * 150 : 0);
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost; bestR = R; bestT = T; bestAcc = nacc; best_smem = total; best_a = a_bytes;
+  // cout block: <= 64 for the 3x3 kernels (27 taps of weights share the stage), up to 256 for 1x1 GEMMs where a larger N
+  // amortises the per-MMA operand fetch (~76 cycles per MMA measured for any N <= 64, scratch/mma_rate.cu)
+  for (int NB = (KS == 1 ? 256 : 64); NB >= 16; NB -= 16) {
+    if (Cout % NB || (nb_must_divide && nb_must_divide % NB)) continue;
+    const uint32_t b_bytes = (uint32_t)taps * 2u * NB * 16u;
+    for (int R = 1; R <= H && R <= 64; ++R) {
+      const int RB = R + 2 * hw;
+      const int T = row_mode ? R : (((R - 1) * PW + WB) + 127) / 128;
+      int nacc = 0;
+      if (2 * T * NB <= 512) nacc = 2;
+      else if (T * NB <= 512) nacc = 1;
+      else continue;
+      uint32_t a_bytes = (uint32_t)KD * 2u * RB * PW * 16u;
+      a_bytes = (a_bytes + 127u) & ~127u;
+      long long over = row_mode ? 0 : ((long long)(128 * T + 2 * hw * PW + 2 * hw) - (long long)RB * PW) * 32;
+      if (over < 0) over = 0;
+      size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
+      int stages = (int)((SMEM_LIMIT - (size_t)over - 1024) / stage);
+      if (stages > MAX_STAGES) stages = MAX_STAGES;
+      if (KS == 3 && stages > 3) stages = 3;
+      if (stages < 2) continue;
+      size_t total = (size_t)stages * stage + (size_t)over + 1024;   // +1024: manual alignment of the dynamic base
+      long long blocks = (H + R - 1) / R;
+      // MMA instructions (each ~max(76, 40 + NB/2) cycles) + halo rows + penalty for un-overlapped epilogue / shallow pipeline
+      long long mma = (NB <= 64 ? 76 : 40 + NB / 2);
+      long long cost = blocks * T * (Cout / NB) * mma * 13 + blocks * RB * 20 * (Cout / NB) + (nacc == 1 ? blocks * T * 150 : 0) +
+                       (KS == 1 && stages < 4 ? blocks * T * 500 : 0);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost; bestR = R; bestT = T; bestAcc = nacc; best_smem = total; best_a = a_bytes; bestNB = NB; bestStages = stages;
+      }
     }
+    if (KS == 3 && best_cost >= 0) break;    // 3x3: take the largest feasible cout block (fewest slab re-reads)
   }
+  const int NB = bestNB;
+  const uint32_t b_bytes = (uint32_t)taps * 2u * NB * 16u;
   if (best_cost < 0) return pl;
   Params& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
   p.up_fd = 0; p.up_cout = 0;
   p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hw; p.T = bestT; p.row_mode = row_mode; p.NB = NB;
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / 16; p.taps = taps;
-  p.nacc = bestAcc;
+  p.nacc = bestAcc; p.stages = bestStages;
   p.a_bytes = best_a;
   p.a_tx_bytes = (uint32_t)KD * 2u * p.RB * PW * 16u;
   p.b_bytes = b_bytes;
