@@ -42,6 +42,9 @@ int ich_conv_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, int dtype
  *      wpack_bf16 = [taps][Cout][Cin] bf16 (K-major per tap).  Requires Cin % 16 == 0, Cout % 16 == 0, Cout <= 256.
  *      ich_conv_tc_supported() returns 1 when the shape is eligible.                                                  */
 int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
+/* which kernel (and therefore which weight pack) a shape uses: 0 none, 1 slab kernel ([kd][kh][kw][Cout][Cin]),
+ * 2 plane-streaming kernel with the depth taps folded into the MMA N dimension ([kh][kw][2-kd][Cout][Cin])            */
+int ich_conv_tc_variant(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
 int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
                     int Cin, int Cout, int KD, int KH, int KW, int relu, void* stream);
 /* same, with the BatchNorm batch statistics (fp64 per-channel sum / sum of squares of the stored outputs) fused into the epilogue */

@@ -1,0 +1,390 @@
+// Plane-streaming tcgen05 convolution (3x3x3, forward and data-gradient): the depth taps are folded into the MMA N dimension.
+//
+// conv_tc.cu loads, for every output plane d, the three input planes d-1, d, d+1 and issues 27 MMAs of N = Cout-block per
+// channel chunk and tile.  Measured on B200 (scratch/mma_rate.cu, profiles/r01_mma_issue_notes.md) an SS-mode MMA costs
+// ~76 cycles for ANY N <= 64 (operand fetch), so small-Cout layers are bound by the NUMBER of MMAs and by the 3x re-read
+// of every input plane.  Here a CTA walks the planes of a column (n, row-block) once:
+//   * input plane p is loaded ONCE (one TMA box, 32-byte swizzled rows as in conv_tc.cu);
+//   * it contributes to the output planes p-1, p, p+1 with the taps kd = 2, 1, 0.  The weights are packed
+//     [kh][kw][kd' = 2-kd][Cout][Cin], so for a fixed (kh, kw) the three depth taps are 3*NB CONSECUTIVE B rows and ONE MMA of
+//     N = 3*NB accumulates into three adjacent accumulator slots (output planes p-1, p, p+1) -- 9 MMAs per plane, tile and
+//     chunk instead of 27, each doing 3x the work for the same A fetch;
+//   * the accumulators are a ring of 4 slots in TMEM ([tile][slot][NB] columns): when plane p has been consumed, output
+//     plane p-1 is complete; the epilogue drains it (bias / ReLU / bf16 / BatchNorm partial sums), zero-fills the slot and
+//     hands it back while the MMAs of the next planes run.  Every MMA accumulates (slots are always zero when acquired).
+//     When the three live slots wrap around the ring the MMA is split in two.
+// Same warp roles / pipeline primitives as conv_tc.cu.  Work item = (n, depth segment of DS planes, row block, w block).
+#include "tc_common.cuh"
+
+namespace {
+
+struct SParams {
+  int N, D, H, W, Cin, Cout;
+  int WB, PW, R, RB, T, row_mode, NB;
+  int n_wb, n_rb, n_nb, KC;
+  int DS, n_ds;
+  int stages;
+  uint32_t a_bytes, a_tx_bytes, b_bytes, stage_bytes, tmem_cols;
+  long long n_items;
+  bf16* y;
+  int y_ld;
+  const float* bias;
+  int relu;
+  double* stat_sum;
+  double* stat_sumsq;
+};
+
+constexpr int S_THREADS = 192;
+constexpr int S_MAX_STAGES = 6;
+constexpr int SLOTS = 4;
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <bool STATS>
+__global__ void __launch_bounds__(S_THREADS, 1)
+conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const SParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[S_MAX_STAGES], empty_bar[S_MAX_STAGES], tfull_bar[SLOTS], tempty_bar[SLOTS];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < SLOTS; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (warp >= 2) {   // all accumulator slots start out zero: every MMA accumulates
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    for (uint32_t c = 0; c < (uint32_t)(p.T * SLOTS * p.NB); c += 16) tmem_st16_zero(lane_base + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const int nb_fixed = (int)(blockIdx.x % p.n_nb);
+  const long long s_begin = blockIdx.x / p.n_nb, s_step = gridDim.x / p.n_nb, n_spatial = p.n_items / p.n_nb;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    int stage = 0; uint32_t phase = 0;
+    for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
+      long long t = sp;
+      const int wb = (int)(t % p.n_wb); t /= p.n_wb;
+      const int rb = (int)(t % p.n_rb); t /= p.n_rb;
+      const int ds = (int)(t % p.n_ds); const int n = (int)(t / p.n_ds);
+      const int w0 = wb * p.WB, h0 = rb * p.R;
+      const int d0 = ds * p.DS, dend = min(p.D, d0 + p.DS);
+      for (int pl = d0 - 1; pl <= dend; ++pl) {
+        if (pl < 0 || pl >= p.D) continue;
+        for (int kc = 0; kc < p.KC; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
+            tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + pl);
+            tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb_fixed * p.NB, 0);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    const uint32_t NB = (uint32_t)p.NB;
+    const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+    const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
+    const uint32_t row16 = ((uint32_t)p.PW * 32u) >> 4;
+    const uint32_t tile16 = (p.row_mode ? (uint32_t)p.PW : 128u) * 2u;
+    const uint32_t tstep = (uint32_t)SLOTS * NB;                      // TMEM columns between consecutive tiles
+    const int T = p.T;
+    int stage = 0; uint32_t phase = 0;
+    long long g_base = 0;                                              // output planes completed by this CTA so far
+    for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
+      long long t = sp / p.n_wb / p.n_rb;
+      const int ds = (int)(t % p.n_ds);
+      const int d0 = ds * p.DS, dend = min(p.D, d0 + p.DS);
+      int acquired = d0 - 1;
+      for (int pl = d0 - 1; pl <= dend; ++pl) {
+        if (pl >= 0 && pl < p.D) {
+          const int lo = max(d0, pl - 1), hi = min(dend - 1, pl + 1);
+          for (int d = acquired + 1; d <= hi; ++d) {                   // first touch of an output plane: its slot must be drained + zeroed
+            const long long g = g_base + (d - d0);
+            mbar_wait(&tempty_bar[g & 3], (uint32_t)(((g >> 2) & 1) ^ 1));
+            acquired = d;
+          }
+          tc_fence_after();
+          for (int kc = 0; kc < p.KC; ++kc) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+            const uint32_t a_lo0 = ((sa & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = (((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            uint32_t a_kh = a_lo0;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                int d = lo;
+                while (d <= hi) {                                       // <= 2 runs of consecutive ring slots
+                  const long long g = g_base + (d - d0);
+                  const int s0 = (int)(g & 3);
+                  const int m = min(hi - d + 1, SLOTS - s0);
+                  const uint32_t brow = (uint32_t)((kh * 3 + kw) * 3 + (d - (pl - 1))) * NB;   // kd' = d - pl + 1
+                  const uint64_t bdesc = pack64(b_lo0 + brow * 2u, desc_hi);
+                  const uint32_t idesc = idesc_base | (((uint32_t)m * NB >> 3) << 17);
+                  uint32_t a_lo = a_kh + 2u * (uint32_t)kw;
+                  uint32_t dcol = tmem_base + (uint32_t)s0 * NB;
+#pragma unroll 4
+                  for (int tt = 0; tt < T; ++tt) {
+                    if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, idesc, 1u);
+                    a_lo += tile16;
+                    dcol += tstep;
+                  }
+                  d += m;
+                }
+              }
+            }
+            __syncwarp();
+            if (elect_one()) umma_commit(&empty_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        const int dc = pl - 1;                                          // output plane completed by this step
+        if (dc >= d0 && dc < dend) {
+          const long long g = g_base + (dc - d0);
+          if (elect_one()) umma_commit(&tfull_bar[g & 3]);
+          __syncwarp();
+        }
+      }
+      g_base += dend - d0;
+    }
+  } else {
+    // ===================================================== epilogue warps (2..5)
+    const int q = warp & 3;
+    const int l = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float csum[STATS ? 64 : 1], csq[STATS ? 64 : 1];
+    if (STATS) {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) csum[k] = csq[k] = 0.f;
+    }
+    const int n0 = nb_fixed * p.NB;
+    long long g_base = 0;
+    for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
+      long long t = sp;
+      const int wb = (int)(t % p.n_wb); t /= p.n_wb;
+      const int rb = (int)(t % p.n_rb); t /= p.n_rb;
+      const int ds = (int)(t % p.n_ds); const int n = (int)(t / p.n_ds);
+      const int w0 = wb * p.WB, h0 = rb * p.R;
+      const int d0 = ds * p.DS, dend = min(p.D, d0 + p.DS);
+      for (int d = d0; d < dend; ++d) {
+        const long long g = g_base + (d - d0);
+        const int slot = (int)(g & 3);
+        mbar_wait(&tfull_bar[slot], (uint32_t)((g >> 2) & 1));
+        tc_fence_after();
+        for (int tt = 0; tt < p.T; ++tt) {
+          const int f = (p.row_mode ? tt * p.PW : tt * 128) + l;
+          const int r = f / p.PW, pos = f - r * p.PW;
+          const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W);
+          const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
+          bf16* yrow = p.y + vox * p.y_ld + n0;
+          const uint32_t taddr = lane_base + (uint32_t)((tt * SLOTS + slot) * p.NB);
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            if (c0 < p.NB) {
+              uint32_t v[16];
+              tmem_ld16(taddr + (uint32_t)c0, v);
+              tmem_ld_wait();
+              tmem_st16_zero(taddr + (uint32_t)c0);                     // hand the slot back zeroed
+              if (valid) {
+                float f32[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  float a = __uint_as_float(v[k]);
+                  if (p.bias) a += p.bias[n0 + c0 + k];
+                  if (p.relu) a = fmaxf(a, 0.f);
+                  f32[k] = a;
+                  if (STATS) {
+                    const float rv = __bfloat162float(__float2bfloat16_rn(a));
+                    csum[c0 + k] += rv;
+                    csq[c0 + k] = fmaf(rv, rv, csq[c0 + k]);
+                  }
+                }
+                Vec<bf16>::store(yrow + c0, f32);
+                Vec<bf16>::store(yrow + c0 + 8, f32 + 8);
+              }
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+      }
+      g_base += dend - d0;
+    }
+    if (STATS) {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        if (k < p.NB) {
+          const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
+          if (lane == 0) {
+            atomicAdd(&p.stat_sum[n0 + k], (double)a);
+            atomicAdd(&p.stat_sumsq[n0 + k], (double)b);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+struct SPlan {
+  bool ok = false;
+  SParams p{};
+  size_t smem_bytes = 0;
+};
+
+SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
+  SPlan pl;
+  if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
+  if (N <= 0 || D < 4 || H <= 0 || W < 4) return pl;
+  int WB;
+  if (W <= 128) WB = W;
+  else if (W % 128 == 0) WB = 128;
+  else return pl;
+  const int PW = WB + 2;
+  int NB = 0;
+  for (int c = 64; c >= 16; c -= 16)
+    if (Cout % c == 0) { NB = c; break; }
+  if (!NB) return pl;
+  const bool row_mode = (WB == 128);
+  const int Tmax = 512 / (SLOTS * NB);
+  const uint32_t b_bytes = 27u * NB * 32u;
+  int bestR = 0, bestT = 0, bestStages = 0;
+  size_t best_smem = 0;
+  uint32_t best_a = 0;
+  long long best_cost = -1;
+  for (int R = 1; R <= H && R <= 64; ++R) {
+    const int RB = R + 2;
+    const int T = row_mode ? R : (((R - 1) * PW + WB) + 127) / 128;
+    if (T > Tmax) break;
+    uint32_t a_bytes = (uint32_t)RB * PW * 32u;
+    a_bytes = (a_bytes + 127u) & ~127u;
+    long long over = row_mode ? 0 : ((long long)(128 * T + 2 * PW + 2) - (long long)RB * PW) * 32;
+    if (over < 0) over = 0;
+    size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
+    int stages = (int)((SMEM_LIMIT - (size_t)over - 1024) / stage);
+    if (stages > S_MAX_STAGES) stages = S_MAX_STAGES;
+    if (stages < 2) continue;
+    size_t total = (size_t)stages * stage + (size_t)over + 1024;
+    long long blocks = (H + R - 1) / R;
+    long long cost = blocks * T * 1000 + blocks * RB * 30;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost; bestR = R; bestT = T; bestStages = stages; best_smem = total; best_a = a_bytes;
+    }
+  }
+  if (best_cost < 0) return pl;
+  SParams& p = pl.p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2; p.T = bestT; p.row_mode = row_mode; p.NB = NB;
+  p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / 16;
+  p.DS = D >= 16 ? 16 : D;
+  p.n_ds = (D + p.DS - 1) / p.DS;
+  p.stages = bestStages;
+  p.a_bytes = best_a;
+  p.a_tx_bytes = (uint32_t)p.RB * PW * 32u;     // bytes the TMA box really delivers (a_bytes is rounded up for alignment)
+  p.b_bytes = b_bytes;
+  p.stage_bytes = (uint32_t)(((size_t)best_a + b_bytes + 1023) & ~(size_t)1023);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(SLOTS * bestT * NB)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.n_items = (long long)N * p.n_ds * p.n_rb * p.n_wb * p.n_nb;
+  pl.smem_bytes = best_smem;
+  pl.ok = true;
+  return pl;
+}
+
+}  // namespace
+
+// Called by conv_tc.cu's entry points (ich_conv_tc_variant decides which kernel a shape uses).
+bool ich_stream_eligible(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
+  const char* e = getenv("ICH_TC_STREAM");
+  if (e && atoi(e) == 0) return false;
+  if (KD != 3 || KH != 3 || KW != 3 || !get_encode()) return false;
+  return make_splan(N, D, H, W, Cin, Cout).ok;
+}
+
+int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W, int Cin,
+                      int Cout, int relu, double* stat_sum, double* stat_sumsq, cudaStream_t stream, const char* what) {
+  SPlan pl = make_splan(N, D, H, W, Cin, Cout);
+  ICH_REQUIRE(pl.ok, "%s: unsupported shape for the plane-streaming kernel", what);
+  ICH_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wpack_bf16 & 15) == 0,
+              "%s: pointers / pitches must be 16-byte aligned (x_ld %d, y_ld %d)", what, x_ld, y_ld);
+  EncodeTiledFn enc = get_encode();
+  SParams& p = pl.p;
+  p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
+  p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
+  if (stat_sum) {
+    ICH_REQUIRE(stat_sumsq != nullptr, "%s: fused statistics need both buffers", what);
+    cudaMemsetAsync(stat_sum, 0, sizeof(double) * Cout, stream);
+    cudaMemsetAsync(stat_sumsq, 0, sizeof(double) * Cout, stream);
+  }
+  CUtensorMap map_x, map_w;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
+    cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2};
+    cuuint32_t box[4] = {16, (cuuint32_t)p.PW, (cuuint32_t)p.RB, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(x) failed with %d", what, (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 27};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[3] = {16, (cuuint32_t)p.NB, 27};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(w) failed with %d", what, (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e != cudaSuccess) cudaGetLastError();
+    ICH_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
+  grid = grid / p.n_nb * p.n_nb;
+  if (grid < p.n_nb) grid = p.n_nb;
+  if (stat_sum) conv_tc_stream_kernel<true><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else conv_tc_stream_kernel<false><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  return ich_check_launch(what);
+}

@@ -75,6 +75,10 @@ def _pack(param, kind):
                 packs[kind] = w.permute(2, 3, 4, 0, 1).reshape(-1, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
             elif kind == 'conv_dgrad_tc':  # [taps'][Cin][Cout] bf16
                 packs[kind] = w.flip(2, 3, 4).permute(2, 3, 4, 1, 0).reshape(-1, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
+            elif kind == 'conv_fwd_tc_s':   # plane-streaming kernel: [kh][kw][2-kd][Cout][Cin] bf16
+                packs[kind] = w.flip(2).permute(3, 4, 2, 0, 1).reshape(-1, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
+            elif kind == 'conv_dgrad_tc_s':  # same for the data-gradient conv (taps flipped, channels transposed)
+                packs[kind] = w.flip(3, 4).permute(3, 4, 2, 1, 0).reshape(-1, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
             elif kind == 'convT_fwd_tc':  # [taps*Cout][Cin] bf16 (B operand of the up-sampling GEMM)
                 packs[kind] = w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).to(torch.bfloat16).contiguous()
             elif kind == 'convT_dgrad_tc':  # [Cin][taps*Cout] bf16 (B operand of the 1x1 data-gradient GEMM)
@@ -93,12 +97,17 @@ def _ksize(weight):
     return w.shape[2], w.shape[3], w.shape[4]
 
 
-def _use_tc(x, cin, cout, k):
+def _tc_variant(x, cin, cout, k):
+    """0: CUDA-core path; 1: slab tcgen05 kernel; 2: plane-streaming tcgen05 kernel (different weight pack)."""
     if not (config.get('tensor_cores') and x.dtype == torch.bfloat16):
-        return False
+        return 0
     from ._lib import lib
     n, d, h, w, _ = x.shape
-    return bool(lib().ich_conv_tc_supported(n, d, h, w, cin, cout, *k))
+    return int(lib().ich_conv_tc_variant(n, d, h, w, cin, cout, *k))
+
+
+def _use_tc(x, cin, cout, k):
+    return _tc_variant(x, cin, cout, k) != 0
 
 
 # bench.py sets PROFILE = [] to collect (kind, flops, start_event, end_event) per conv kernel launch
@@ -138,9 +147,10 @@ def _conv_forward(x, weight, bias, relu):
     k = _ksize(weight)
     y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=x.device)
     xp, xld = _rows(x)
-    if _use_tc(x, cin, cout, k):
-        call('ich_conv_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd_tc')), _p(bias), y.data_ptr(), cout, n, d, h, w, cin, cout, *k,
-             int(relu), _stream())
+    var = _tc_variant(x, cin, cout, k)
+    if var:
+        call('ich_conv_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd_tc_s' if var == 2 else 'conv_fwd_tc')), _p(bias), y.data_ptr(), cout,
+             n, d, h, w, cin, cout, *k, int(relu), _stream())
     else:
         call('ich_conv_fwd', xp, xld, _p(_pack(weight, 'conv_fwd')), _p(bias), y.data_ptr(), cout, _dt(x), n, d, h, w, cin, cout, *k,
              int(relu), _stream())
@@ -161,8 +171,10 @@ def _conv_dgrad(dy, weight):
     k = _ksize(weight)
     dx = torch.empty((n, d, h, w, cin), dtype=dy.dtype, device=dy.device)
     yp, yld = _rows(dy)
-    if _use_tc(dy, cout, cin, k):
-        call('ich_conv_tc_fwd', yp, yld, _p(_pack(weight, 'conv_dgrad_tc')), None, dx.data_ptr(), cin, n, d, h, w, cout, cin, *k, 0, _stream())
+    var = _tc_variant(dy, cout, cin, k)
+    if var:
+        call('ich_conv_tc_fwd', yp, yld, _p(_pack(weight, 'conv_dgrad_tc_s' if var == 2 else 'conv_dgrad_tc')), None, dx.data_ptr(), cin,
+             n, d, h, w, cout, cin, *k, 0, _stream())
     else:
         call('ich_conv_fwd', yp, yld, _p(_pack(weight, 'conv_dgrad')), None, dx.data_ptr(), cin, _dt(dy), n, d, h, w, cout, cin, *k, 0, _stream())
     return dx
@@ -271,12 +283,13 @@ class ConvBnRelu(Function):
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)      # scale, shift, mean, invstd
         sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
         k = _ksize(weight)
-        if training and k[1] == 3 and _use_tc(x, cin, cout, k):
+        var = _tc_variant(x, cin, cout, k) if (training and k[1] == 3) else 0
+        if var:
             # tcgen05 conv with the batch statistics accumulated in its epilogue (no separate pass over y)
             y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=dev)
             xp, xld = _rows(x)
             with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
-                call('ich_conv_tc_fwd_stats', xp, xld, _p(_pack(weight, 'conv_fwd_tc')), y.data_ptr(), cout, sums[0].data_ptr(),
+                call('ich_conv_tc_fwd_stats', xp, xld, _p(_pack(weight, 'conv_fwd_tc_s' if var == 2 else 'conv_fwd_tc')), y.data_ptr(), cout, sums[0].data_ptr(),
                      sums[1].data_ptr(), n, d, h, w, cin, cout, *k, _stream())
         else:
             y = conv_forward(x, weight, None)

@@ -370,6 +370,8 @@ TC_CASES = [  # N, D, H, W, Cin, Cout, k3d  -- shapes the tcgen05 kernel must ta
     (1, 1, 20, 256, 32, 32, False),     # 2-D, two w-blocks, H not a multiple of R
     (1, 6, 128, 128, 32, 32, True),     # > 148 work items: several items per persistent CTA (pipeline phases wrap)
     (1, 5, 10, 24, 48, 48, True),       # odd sizes: W = 24, 48 channels (NB = 48)
+    (1, 20, 8, 32, 32, 128, True),      # plane-streaming kernel: 2 depth segments (16 + 4 planes), 2 cout blocks
+    (2, 18, 4, 128, 16, 16, True),      # plane-streaming kernel, row mode, NB = 16, ring wraps many times
 ]
 
 
