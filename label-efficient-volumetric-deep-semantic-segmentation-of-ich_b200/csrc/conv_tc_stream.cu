@@ -335,6 +335,10 @@ bool ich_stream_eligible(int N, int D, int H, int W, int Cin, int Cout, int KD, 
   const char* e = getenv("ICH_TC_STREAM");
   if (e && atoi(e) == 0) return false;
   if (KD != 3 || KH != 3 || KW != 3 || !get_encode()) return false;
+  // Measured (profiles/r01_conv_layers.txt): the streaming kernel wins on the full-resolution layers (row-exact 128-wide
+  // tiles, big planes: 1.3-1.6x) and loses on the small planes of the deeper levels, where the per-plane weight reload and the
+  // TMEM limit on tiles per item (4 slots) dominate.  ICH_TC_STREAM=2 forces it everywhere (tests).
+  if (!(e && atoi(e) == 2) && W % 128 != 0) return false;
   return make_splan(N, D, H, W, Cin, Cout).ok;
 }
 
