@@ -18,7 +18,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.d
 if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 
-from ich_b200 import ops  # noqa: E402
+from ich_b200 import config as _cfg, ops  # noqa: E402
 
 
 def _dropout_list(p_dropout, depth):
@@ -60,20 +60,25 @@ class ConvBlock(nn.Module):
         self.conv2 = conv(in_channels=mid_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1)
         self.bn2 = bn(out_channels)
 
-    def _unit(self, x, conv, bn):
+    def _unit(self, x, conv, bn, concat_c=0):
         if conv.padding[0] * 2 + 1 != conv.kernel_size[0]:
             _not_built(f'kernel_size={conv.kernel_size} with padding={conv.padding}')
         training = self.training or not bn.track_running_stats
-        z = ops.ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, True)
+        z = ops.ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, True, concat_c)
+        if concat_c:
+            z, buf = z
+            z._ich_concat_buf = buf          # the decoder's UpConvCat completes this buffer in place (zero-copy skip concat)
         if training and bn.track_running_stats:
             bn.num_batches_tracked += 1
         return z
 
-    def forward_cl(self, x):
-        """Channel-last engine path: x [N, D, H, W, C] in the engine dtype."""
+    def forward_cl(self, x, concat_c=0):
+        """Channel-last engine path: x [N, D, H, W, C] in the engine dtype. concat_c > 0: the block output is laid out as the
+        first channel slab of a [.., C + concat_c] buffer (it will be the skip half of a decoder concat)."""
+        use_dropout = self.dropout.p > 0.0 and self.training
         x = self._unit(x, self.conv1, self.bn1)
-        x = self._unit(x, self.conv2, self.bn2)
-        if self.dropout.p > 0.0 and self.training:
+        x = self._unit(x, self.conv2, self.bn2, 0 if use_dropout else concat_c)
+        if use_dropout:
             x = self.dropout(x)      # elementwise, RNG-dependent (SURVEY section 7): torch's Philox dropout on the engine tensor
         return x
 
@@ -160,8 +165,14 @@ class _UNetBase(nn.Module):
     def _encode(self, x):
         self._check_grid(x, len(self.down_block))
         res = []
-        for block in self.down_block:                       # UNet.py:106-109
-            x = block.forward_cl(x)
+        n_down = len(self.down_block)
+        ups = list(getattr(self, 'up_samp', []))
+        for i, block in enumerate(self.down_block):         # UNet.py:106-109
+            # skip tensor i is consumed by decoder stage (n_down - 1 - i): lay it out inside that stage's concat buffer
+            j = n_down - 1 - i
+            concat_c = ups[j].out_channels if (_cfg.get('zero_copy_concat') and j < len(ups)
+                                               and isinstance(ups[j], (nn.ConvTranspose3d, nn.ConvTranspose2d))) else 0
+            x = block.forward_cl(x, concat_c)
             res.append(x)
             x = ops.MaxPool2.apply(x, self._fd)
         return self.bottleneck_block.forward_cl(x), res     # UNet.py:112
@@ -170,7 +181,7 @@ class _UNetBase(nn.Module):
         for up, block, r in zip(self.up_samp, self.up_block, res[::-1]):     # UNet.py:117-119
             if not isinstance(up, (nn.ConvTranspose3d, nn.ConvTranspose2d)):
                 _not_built('bilinear=True (nn.Upsample decoder)')
-            x = block.forward_cl(ops.UpConvCat.apply(x, r, up.weight, up.bias, self._fd))
+            x = block.forward_cl(ops.UpConvCat.apply(x, r, up.weight, up.bias, self._fd, getattr(r, '_ich_concat_buf', None)))
         return x
 
 

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd, long long M, int C,
                                                                  int relu, double* __restrict__ sums) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = 4;                       // rows in flight per thread: 8 independent 16-byte loads
   const int groups = C / V, rpb = 256 / groups;
   const int c = (threadIdx.x % groups) * V;
   float sc[V], sf[V], mu[V], is[V], sb[V], sg[V];
@@ -332,25 +333,25 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
   for (int k = 0; k < V; ++k) { sc[k] = scale[c + k]; sf[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; sb[k] = sg[k] = 0.f; }
   const long long step = (long long)gridDim.x * rpb;
   long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
-  for (; r + step < M; r += 2 * step) {
-    float a0[V], b0[V], a1[V], b1[V];
-    Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
-    Vec<T>::load(dz + (r + step) * dz_ld + c, a1); Vec<T>::load(y + (r + step) * y_ld + c, b1);
+  for (; r + (U - 1) * step < M; r += U * step) {
+    float a[U][V], b[U][V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
-      float g1 = (!relu || fmaf(b1[k], sc[k], sf[k]) > 0.f) ? a1[k] : 0.f;
-      sb[k] += g0 + g1;
-      sg[k] = fmaf(g0, (b0[k] - mu[k]) * is[k], sg[k]);
-      sg[k] = fmaf(g1, (b1[k] - mu[k]) * is[k], sg[k]);
-    }
+    for (int u = 0; u < U; ++u) { Vec<T>::load(dz + (r + u * step) * dz_ld + c, a[u]); Vec<T>::load(y + (r + u * step) * y_ld + c, b[u]); }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float g0 = (!relu || fmaf(b[u][k], sc[k], sf[k]) > 0.f) ? a[u][k] : 0.f;
+        sb[k] += g0;
+        sg[k] = fmaf(g0, (b[u][k] - mu[k]) * is[k], sg[k]);
+      }
   }
-  if (r < M) {
+  for (; r < M; r += step) {
     float a0[V], b0[V];
     Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
+      const float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
       sb[k] += g0;
       sg[k] = fmaf(g0, (b0[k] - mu[k]) * is[k], sg[k]);
     }

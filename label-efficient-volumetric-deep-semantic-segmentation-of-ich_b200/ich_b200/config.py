@@ -10,6 +10,8 @@ _state = {
     # compute d(loss)/d(input) when the caller set input.requires_grad_ (models/optim/UNet2D.py:137). The reference
     # trainers never read it; default off saves the first layer's data-gradient.
     'input_grad': os.environ.get('ICH_B200_INPUT_GRAD', '0') == '1',
+    # lay encoder skip tensors out inside the decoder's concat buffer (no copy for torch.cat([res, up], 1))
+    'zero_copy_concat': os.environ.get('ICH_B200_ZERO_COPY_CONCAT', '0') == '1',   # measured slower (strided 2C-pitch reads) -> off
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

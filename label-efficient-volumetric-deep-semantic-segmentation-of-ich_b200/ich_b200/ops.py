@@ -50,6 +50,13 @@ def _dt(t):
     return config.dtype_code(t.dtype)
 
 
+def _alias(buf, shape, strides, offset=0):
+    """Fresh tensor over `buf`'s storage (own autograd version counter): lets one Function write a channel slab of a buffer
+    that another Function's saved tensors alias, without tripping autograd's in-place checks. The kernels, not torch, do
+    the writes, and the slabs never overlap."""
+    return torch.empty(0, dtype=buf.dtype, device=buf.device).set_(buf.untyped_storage(), buf.storage_offset() + offset, shape, strides)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # weight packs (derived caches, never serialised; invalidated when the optimizer mutates the parameter in place)
 # ---------------------------------------------------------------------------------------------------------------
@@ -274,7 +281,7 @@ def from_channels_last(x, was_4d=False):
 # ---------------------------------------------------------------------------------------------------------------
 class ConvBnRelu(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, relu):
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, relu, concat_c=0):
         n, d, h, w, cin = x.shape
         cout = weight.shape[0]
         m = n * d * h * w
@@ -298,24 +305,41 @@ class ConvBnRelu(Function):
         call('ich_bn_finalize', sums[0].data_ptr(), sums[1].data_ptr(), m, cout, _p(gamma), _p(beta), _p(bias), _p(running_mean),
              _p(running_var), BN_MOMENTUM, BN_EPS, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
              int(training), _stream())
-        z = torch.empty_like(y)
-        call('ich_affine_act', y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), z.data_ptr(), cout, _dt(y), m, cout, int(relu),
+        if concat_c:
+            # zero-copy skip connection: z is written as the first channel slab of the [.., cout + concat_c] buffer that the
+            # decoder's ConvTranspose later completes (torch.cat([res, up], 1) of reference UNet.py:119 without the copy)
+            ctot = cout + concat_c
+            buf = torch.empty((n, d, h, w, ctot), dtype=y.dtype, device=dev)
+            z = _alias(buf, (n, d, h, w, cout), (d * h * w * ctot, h * w * ctot, w * ctot, ctot, 1))
+            zld = ctot
+        else:
+            buf = None
+            z = torch.empty_like(y)
+            zld = cout
+        call('ich_affine_act', y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), z.data_ptr(), zld, _dt(y), m, cout, int(relu),
              _stream())
         ctx.save_for_backward(x, weight, y, stats)
         ctx.training, ctx.relu = training, relu
+        if concat_c:
+            ctx.mark_non_differentiable(buf)
+            return z, buf
         return z
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, *unused):
         x, weight, y, stats = ctx.saved_tensors
         n, d, h, w, cout = y.shape
         m = n * d * h * w
-        dz = dz.contiguous()
+        try:
+            dzp, dzld = _rows(dz)
+        except RuntimeError:
+            dz = dz.contiguous()
+            dzp, dzld = dz.data_ptr(), cout
         dy = torch.empty_like(y)
         sums = torch.empty((2, cout), dtype=torch.float64, device=y.device)
         dgamma = torch.empty(cout, dtype=torch.float32, device=y.device)
         dbeta = torch.empty(cout, dtype=torch.float32, device=y.device)
-        call('ich_bn_act_bwd', dz.data_ptr(), cout, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+        call('ich_bn_act_bwd', dzp, dzld, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
              stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(), _dt(y), m, cout, int(ctx.relu),
              int(ctx.training), _stream())
         need = ctx.needs_input_grad
@@ -325,7 +349,7 @@ class ConvBnRelu(Function):
         if need[2]:
             # training: d(loss)/d(bias) is exactly 0 (BatchNorm removes the mean); eval: sum of dy
             db = torch.zeros(cout, dtype=torch.float32, device=y.device) if ctx.training else col_sum(dy).float()
-        return dx, dw, db, (dgamma if need[3] else None), (dbeta if need[4] else None), None, None, None, None
+        return dx, dw, db, (dgamma if need[3] else None), (dbeta if need[4] else None), None, None, None, None, None
 
 
 class ConvBias(Function):
@@ -395,17 +419,21 @@ class MaxPool2(Function):
 # ---------------------------------------------------------------------------------------------------------------
 class UpConvCat(Function):
     @staticmethod
-    def forward(ctx, x, res, weight, bias, fd):
+    def forward(ctx, x, res, weight, bias, fd, buf=None):
         n, d, h, w, cin = x.shape
         cout = weight.shape[1]
         cres = res.shape[-1]
         ctot = cres + cout
-        out = torch.empty((n, d * fd, h * 2, w * 2, ctot), dtype=x.dtype, device=x.device)
-        if tuple(res.shape[:4]) != tuple(out.shape[:4]):
-            raise RuntimeError(f'ich_b200: skip tensor {tuple(res.shape)} does not match the up-sampled grid {tuple(out.shape)}')
-        m_out = out.numel() // ctot
-        rp, rld = _rows(res)
-        call('ich_slab_copy', rp, rld, out.data_ptr(), ctot, _dt(x), m_out, cres, _stream())
+        oshape = (n, d * fd, h * 2, w * 2, ctot)
+        if tuple(res.shape[:4]) != oshape[:4]:
+            raise RuntimeError(f'ich_b200: skip tensor {tuple(res.shape)} does not match the up-sampled grid {oshape}')
+        m_out = oshape[0] * oshape[1] * oshape[2] * oshape[3]
+        if buf is not None and tuple(buf.shape) == oshape and buf.dtype == x.dtype and buf.is_contiguous() and res.data_ptr() == buf.data_ptr():
+            out = _alias(buf, oshape, buf.stride())      # the skip half is already in place (ConvBnRelu wrote it there)
+        else:
+            out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+            rp, rld = _rows(res)
+            call('ich_slab_copy', rp, rld, out.data_ptr(), ctot, _dt(x), m_out, cres, _stream())
         up = out[..., cres:]
         xp, xld = _rows(x)
         from ._lib import lib
@@ -435,8 +463,7 @@ class UpConvCat(Function):
         need = ctx.needs_input_grad
         dres = None
         if need[1]:
-            dres = torch.empty(dout.shape[:4] + (cres,), dtype=dout.dtype, device=dout.device)
-            call('ich_slab_copy', dout.data_ptr(), ctot, dres.data_ptr(), cres, _dt(dout), m_out, cres, _stream())
+            dres = dout[..., :cres]                      # zero-copy: consumers take the channel pitch explicitly
         dup = dout[..., cres:]
         dx = dw = db = None
         if ctx.use_tc and (need[0] or need[2]):
@@ -465,7 +492,7 @@ class UpConvCat(Function):
             s = torch.empty(cout, dtype=torch.float64, device=x.device)
             call('ich_colstats', dup.data_ptr(), ctot, _dt(dout), m_out, cout, s.data_ptr(), None, _stream())
             db = s.float()
-        return dx, dres, dw, db, None
+        return dx, dres, dw, db, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------

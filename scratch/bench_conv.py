@@ -39,3 +39,28 @@ for name, n, d, h, w, cin, cout in LAYERS:
 for k, (f, ms) in tot.items():
     if ms:
         print(f'total {k}: {ms:.2f} ms, {f / ms / 1e9:.1f} TF/s')
+
+# fused-statistics variant of the forward (what ConvBnRelu uses in training)
+if os.environ.get('BENCH_STATS'):
+    from ich_b200._lib import call
+    tot = [0.0, 0.0]
+    for name, n, d, h, w, cin, cout in LAYERS:
+        x = torch.randn(n, d, h, w, cin, device='cuda', dtype=torch.bfloat16)
+        wt = torch.randn(cout, cin, 3, 3, 3, device='cuda') * 0.05
+        y = torch.empty(n, d, h, w, cout, device='cuda', dtype=torch.bfloat16)
+        sums = torch.empty(2, cout, device='cuda', dtype=torch.float64)
+        var = ops._tc_variant(x, cin, cout, (3, 3, 3))
+        pk = ops._pack(wt, 'conv_fwd_tc_s' if var == 2 else 'conv_fwd_tc')
+        fn = lambda: call('ich_conv_tc_fwd_stats', x.data_ptr(), cin, pk.data_ptr(), y.data_ptr(), cout, sums[0].data_ptr(), sums[1].data_ptr(),
+                          n, d, h, w, cin, cout, 3, 3, 3, torch.cuda.current_stream().cuda_stream)
+        fn(); fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n * d * h * w * cin * cout * 27
+        tot[0] += fl; tot[1] += ms
+        print(f'{name} fwd+stats {ms:7.3f} ms {fl / ms / 1e9:7.1f} TF/s (variant {var})')
+    print(f'total fwd+stats: {tot[1]:.2f} ms, {tot[0] / tot[1] / 1e9:.1f} TF/s')

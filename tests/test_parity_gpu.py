@@ -286,6 +286,24 @@ def test_unet3d_end_to_end_fp32(golden):
         assert torch.equal((ev >= 0.5).cpu(), fx['out_eval'] >= 0.5)
 
 
+def test_zero_copy_concat_matches_copying_path(golden):
+    """Optional layout (ICH_B200_ZERO_COPY_CONCAT=1): skip tensors written straight into the decoder's concat buffer must give
+    the same forward / backward as the copying path (fp32 mode: identical kernels, identical values)."""
+    from src.models.networks.UNet import UNet
+    from src.models.optim.LossFunctions import ComboLoss
+    fx = golden('unet3d_combo.pt')
+    res = []
+    for zc in (False, True):
+        with config.override(precision='fp32', zero_copy_concat=zc):
+            net = _load(UNet, fx)
+            out = net(fx['x'].to(DEV))
+            ComboLoss(**fx['loss_kwargs'])(out, fx['mask'].to(DEV)).backward()
+            res.append((out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
+    assert torch.equal(res[0][0], res[1][0])
+    for k in res[0][1]:
+        assert rel(res[1][1][k], res[0][1][k]) < 1e-5 or res[0][1][k].abs().max() == 0, k
+
+
 def test_unet3d_end_to_end_bf16(golden):
     from src.models.networks.UNet import UNet
     from src.models.optim.LossFunctions import ComboLoss
