@@ -430,3 +430,77 @@ def test_conv_tcgen05_fwd_dgrad(case):
     # element-wise: never more than one bf16 ulp-ish away from the FFMA kernel's result (same operands, fp32 accumulate)
     diff = (y.float() - y_ffma.float()).abs()
     assert (diff <= 2e-2 * y_ffma.float().abs() + 1e-3).all(), diff.max().item()
+
+
+def test_sliding_window_inference_fp32_matches_oracle(golden):
+    """cfg-5 (shrunk): eval-mode drop-in network applied window by window with mean blending == the oracle's stitching of the
+    oracle network; masks (pred >= 0.5) bit-exact in the fp32 verification mode."""
+    from ich_b200 import infer
+    from src.models.networks.UNet import UNet
+    fx = golden('unet3d_combo.pt')
+    sd = fx['state_dict_after']
+    vol = torch.rand(1, 1, 8, 32, 32, generator=torch.Generator().manual_seed(11))
+    with config.override(precision='fp32'):
+        net = UNet(**fx['kwargs'])
+        net.load_state_dict(sd)
+        net = net.to(DEV).eval()
+        for window, stride in (((8, 16, 16), (8, 16, 16)), ((8, 16, 16), (8, 8, 8)), ((4, 16, 32), (4, 8, 32))):
+            pred, mask = infer.sliding_window_predict(net, vol.to(DEV), window, stride, batch=3, distributed=False)
+            want, wmask = UO.sliding_window_predict(vol, sd, window, stride)
+            assert rel(pred, want) < 1e-4
+            assert torch.equal(mask.cpu(), wmask)
+        assert not net.training
+
+
+def test_training_loop_checkpoint_and_frozen_transfer(golden):
+    """The reference trainer protocol on top of the drop-in (models/optim/UNet2D.py:102-176, Contrastive.py:227-253):
+    Adam + ExponentialLR steps reduce the loss, a state-dict checkpoint round-trips, transferred-and-frozen encoder
+    parameters receive no gradient and do not move."""
+    from src.models.networks.UNet import UNet, UNet_Encoder
+    from src.models.optim.LossFunctions import ComboLoss
+    fx = golden('unet3d_combo.pt')
+    with config.override(precision='fp32'):
+        torch.manual_seed(0)
+        net = UNet(**fx['kwargs']).to(DEV).train()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-2, weight_decay=1e-6)
+        sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9)
+        lossf = ComboLoss(**fx['loss_kwargs'])
+        x, m = fx['x'].to(DEV), fx['mask'].to(DEV)
+        losses = []
+        for _ in range(6):
+            xi, mi = x.clone().float().requires_grad_(True), m.clone().float().requires_grad_(True)   # as UNet2D.py:137-138
+            opt.zero_grad()
+            loss = lossf(net(xi), mi)
+            loss.backward()
+            opt.step()
+            sched.step()
+            losses.append(loss.item())
+        assert losses[-1] < losses[0]
+        assert int(net.down_block[0].bn1.num_batches_tracked) == 6
+        ckpt = {'net_state': net.state_dict(), 'optimizer_state': opt.state_dict()}
+        net2 = UNet(**fx['kwargs']).to(DEV)
+        net2.load_state_dict(ckpt['net_state'])
+        net.eval(); net2.eval()
+        with torch.no_grad():
+            assert torch.equal(net(x), net2(x))
+        # transfer + freeze (encoder weights into a full U-Net), as Contrastive.transfer_weights does with rgetattr
+        enc = UNet_Encoder(depth=3, use_3D=True, in_channels=1, MLP_head=[16, 8], top_filter=8, midchannels_factor=2, p_dropout=0.0).to(DEV)
+        tgt = UNet(**fx['kwargs']).to(DEV).train()
+        shared = {k: v for k, v in enc.state_dict().items() if k in tgt.state_dict()}
+        assert len(shared) > 20
+        tgt.load_state_dict({**tgt.state_dict(), **shared})
+        frozen = []
+        for k in shared:
+            obj = tgt
+            for part in k.split('.'):
+                obj = getattr(obj, part)
+            if obj.is_floating_point() and isinstance(obj, torch.nn.Parameter):
+                obj.requires_grad = False
+                frozen.append(obj)
+        before = [p.detach().clone() for p in frozen]
+        opt = torch.optim.Adam([p for p in tgt.parameters() if p.requires_grad], lr=1e-2)
+        lossf(tgt(x), m).backward()
+        opt.step()
+        assert all(p.grad is None for p in frozen)
+        assert all(torch.equal(a, b) for a, b in zip(before, frozen))
+        assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in tgt.up_block.parameters())
