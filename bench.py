@@ -29,6 +29,24 @@ WORKLOAD = 'cfg-3: 3D U-Net depth4 tf32 mcf2, batch 8/GPU of 1x64x128x128, Combo
 CONV_FLOP_PER_STEP = 9118.5e9            # SURVEY section 8d, algorithmic 2*M*N*K x3 (fwd + dgrad + wgrad), per GPU-step
 
 
+def ncu_traffic():
+    """DRAM bytes of the dominant conv launch (u2.c1 forward, 64->32 @ 8x64x128x128) from the committed `ncu --set full` extract:
+    dram__bytes_read.sum + dram__bytes_write.sum (profiles/r01_ncu_conv_stream_u2c1_raw.csv). Algorithmic bytes of that launch:
+    input 1.074 GB + output 0.537 GB (bf16, each touched once)."""
+    try:
+        import csv
+        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_conv_stream_u2c1_raw.csv'))))
+        hdr, units, first = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            i = hdr.index(name)
+            scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[units[i]]
+            tot += float(first[i]) * scale
+        return tot
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
@@ -260,7 +278,8 @@ def main():
                     'd2h_bytes_per_step': 4, 'ms_per_step': 1e3 * t_e2e / args.steps},
             'gpu_launches': launches,
             'roofline': {'bound': 'tensor', 'kernel': 'implicit-GEMM conv fwd+dgrad+wgrad (all launches of the step)', 'achieved': achieved,
-                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf if peak_tf else None, 'traffic': None,
+                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf if peak_tf else None, 'traffic': ncu_traffic(),
+                         'traffic_note': 'DRAM bytes of the largest conv launch (u2.c1 fwd) from ncu --set full; algorithmic 1.61e9',
                          'peak_source': pk_src + ' (sustained)', 'conv_ms_per_step': conv_ms / max(1, min(args.steps, 3)),
                          'conv_share_of_step': conv_ms / (t_prof * 1e3) if t_prof else None,
                          'by_kind_tflops': {k: (a[0] / (a[1] * 1e-3) / 1e12 if a[1] else 0.0) for k, a in by_kind.items()}},
