@@ -518,9 +518,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           for (int pl = 0; pl < p.KD; ++pl) {
             const int dd = d + pl - (p.KD == 3 ? 1 : 0);
             const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
-            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2, cb * p.chunks_u, coord);
+            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2, cb * (p.CU / 16), coord);
           }
-          tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * p.chunks_v, n * p.D + d);
+          tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / 16), n * p.D + d);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -530,20 +530,24 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     {
       // both operands MN-major (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = NB
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
-      // descriptor = {lo: start>>4 | (LBO = 128 B)<<16, hi: SBO>>4 | version}; per MMA only `lo` changes (one add + one pack)
-      const uint32_t a_hi = (((uint32_t)p.RB * p.PW * 16u) >> 4) | (1u << 14);   // SBO = 8-channel chunk stride of x (uniform across planes)
-      const uint32_t b_hi = (((uint32_t)p.R * p.WB * 16u) >> 4) | (1u << 14);    // SBO = 8-channel chunk stride of dy
-      const uint32_t PW = (uint32_t)p.PW, WB = (uint32_t)p.WB, NB = (uint32_t)p.NB;
+      // MN-major SWIZZLE_32B operands: a position is a 32-byte row of 16 channels; 16-channel blocks are LBO apart (uniform
+      // across the planes of the x slab), 8-position groups SBO = 256 B apart.  descriptor = {lo: start>>4 | LBO>>4 << 16,
+      // hi: SBO>>4 | version | layout}; per MMA only the start changes (one add + one pack).  All offsets below are in 16-byte units.
+      const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);
+      const uint32_t a_lbo = (((uint32_t)p.RB * p.PW * 32u) >> 4) << 16;
+      const uint32_t b_lbo = (((uint32_t)p.R * p.WB * 32u) >> 4) << 16;
+      const uint32_t a_hi = desc_hi, b_hi = desc_hi;
+      const uint32_t PW = 2u * (uint32_t)p.PW, WB = 2u * (uint32_t)p.WB, NB = (uint32_t)p.NB;   // row pitches in 16-byte units
       int stage = 0; uint32_t phase = 0;
       uint32_t accum = 0u;
       for (long long item = it_begin; item < it_end; ++item) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        uint32_t a_row = ((sa & 0x3FFFFu) >> 4) | (8u << 16);                      // one position = 16 B = 1 unit
-        uint32_t b_row = (((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (8u << 16);
+        uint32_t a_row = ((sa & 0x3FFFFu) >> 4) | a_lbo;                           // one position = 32 B = 2 units
+        uint32_t b_row = (((sa + p.a_bytes) & 0x3FFFFu) >> 4) | b_lbo;
         for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, b_row += WB) {
-          for (uint32_t s16 = 0; s16 < WB; s16 += 16) {
+          for (uint32_t s16 = 0; s16 < WB; s16 += 32) {                            // 16 positions per MMA
             const uint64_t bdesc = pack64(b_row + s16, b_hi);
             uint32_t a_kh = a_row + s16;
             uint32_t dcol = tmem_base;
@@ -551,7 +555,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             for (int kh = 0; kh < KS; ++kh, a_kh += PW) {
 #pragma unroll
               for (int kw = 0; kw < KS; ++kw) {
-                if (elect_one()) umma_bf16(dcol, pack64(a_kh + (uint32_t)kw, a_hi), bdesc, idesc, accum);
+                if (elect_one()) umma_bf16(dcol, pack64(a_kh + 2u * (uint32_t)kw, a_hi), bdesc, idesc, accum);
                 dcol += NB;
               }
             }
@@ -634,7 +638,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
     const int pw = wb + 2 * hw;
     for (int R = 1; R <= H + 1 && R <= 32; ++R) {
       const int RB = R + 2 * hw;
-      if ((chunks_u * RB) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
+      if (((CU / 16) * RB * pw) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
       size_t a = (size_t)KD * chunks_u * RB * pw * 16;
       size_t b = (size_t)chunks_v * R * wb * 16;
       size_t stage = (a + b + 1023) & ~(size_t)1023;
@@ -694,19 +698,20 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
   CUtensorMap map_x, map_dy;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   {
-    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)N * D};
-    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, 16, (cuuint64_t)H * W * x_ld * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)p.chunks_u, 1};
+    // (c16, W, H, C/16, N*D): the box lands as [16-channel block][row][pos][16 ch] = 32-byte swizzled rows (full L2 sectors)
+    cuuint64_t dims[5] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 16), (cuuint64_t)N * D};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, 32, (cuuint64_t)H * W * x_ld * 2};
+    cuuint32_t box[5] = {16, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)(p.CU / 16), 1};
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(x) failed with %d", what, (int)r);
   }
   {
-    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 8), (cuuint64_t)N * D};
-    cuuint64_t strides[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, 16, (cuuint64_t)H * W * dy_ld * 2};
-    cuuint32_t box[5] = {8, (cuuint32_t)p.WB, (cuuint32_t)p.R, (cuuint32_t)p.chunks_v, 1};
+    cuuint64_t dims[5] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 16), (cuuint64_t)N * D};
+    cuuint64_t strides[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, 32, (cuuint64_t)H * W * dy_ld * 2};
+    cuuint32_t box[5] = {16, (cuuint32_t)p.WB, (cuuint32_t)p.R, (cuuint32_t)(p.NB / 16), 1};
     CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy) failed with %d", what, (int)r);
   }
   static bool attr_set = false;
