@@ -461,7 +461,9 @@ namespace {
 
 struct WParams {
   int N, D, H, W, Cin, Cout, KD, KS;
-  int out_mode, up_cout, taps_out;   // out_mode 1: transposed-conv layout dW[ci][co][tap], columns n = tap*up_cout + co
+  int out_mode, up_cout, taps_out;   // out_mode 1: transposed-conv layout dW[ci][co][tap], columns n = tap*up_cout + co;
+                                     // out_mode 2: operands swapped (U = dy, V = x): rows = co, columns = ci, taps flipped
+  int khs;                           // kh-split: a CTA handles ONE kernel row kh (3 accumulators -> N up to 128); grid.y = pairs * 3
   int WB, PW, R, RB, CU, NB, chunks_u, chunks_v;
   int n_wb, n_rb, n_cb, n_nb;
   uint32_t plane_bytes, a_bytes, b_bytes, stage_bytes, tmem_cols;
@@ -494,7 +496,10 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  const int pair = blockIdx.y;
+  const int n_pairs = p.n_cb * p.n_nb;
+  const int pair = blockIdx.y % n_pairs;
+  const int khf = p.khs ? (int)(blockIdx.y / n_pairs) : 0;      // the kernel row of this CTA in kh-split mode
+  const int khn = p.khs ? 1 : KS;                               // kernel rows accumulated by this CTA
   const int cb = pair / p.n_nb, nb = pair % p.n_nb;
   const long long per = (p.n_pos_items + p.splits - 1) / p.splits;
   const long long it_begin = (long long)blockIdx.x * per;
@@ -518,7 +523,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           for (int pl = 0; pl < p.KD; ++pl) {
             const int dd = d + pl - (p.KD == 3 ? 1 : 0);
             const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
-            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2, cb * (p.CU / 16), coord);
+            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2 + khf, cb * (p.CU / 16), coord);
           }
           tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / 16), n * p.D + d);
         }
@@ -551,8 +556,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const uint64_t bdesc = pack64(b_row + s16, b_hi);
             uint32_t a_kh = a_row + s16;
             uint32_t dcol = tmem_base;
-#pragma unroll
-            for (int kh = 0; kh < KS; ++kh, a_kh += PW) {
+            for (int kh = 0; kh < khn; ++kh, a_kh += PW) {
 #pragma unroll
               for (int kw = 0; kw < KS; ++kw) {
                 if (elect_one()) umma_bf16(dcol, pack64(a_kh + 2u * (uint32_t)kw, a_hi), bdesc, idesc, accum);
@@ -578,8 +582,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int taps = p.KD * KS * KS;
     mbar_wait(&done_bar, 0);
     tc_fence_after();
-    for (int j = 0; j < KS * KS; ++j) {
-      const int tap = kd * KS * KS + j;
+    for (int j = 0; j < khn * KS; ++j) {
+      const int tap = kd * KS * KS + khf * KS + j;
       for (int c0 = 0; c0 < p.NB; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.NB + c0), v);
@@ -590,6 +594,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const int col = nb * p.NB + c0 + k;
             size_t idx;
             if (p.out_mode == 0) idx = ((size_t)col * p.Cin + ci) * taps + tap;                    // conv: dW[co][ci][tap]
+            else if (p.out_mode == 2) idx = ((size_t)ci * p.Cout + col) * taps + (taps - 1 - tap);  // swapped: rows = co ("ci" here), cols = ci
             else { const int t2 = col / p.up_cout; idx = ((size_t)ci * p.up_cout + (col - t2 * p.up_cout)) * p.taps_out + t2; }   // convT: dW[ci][co][tap]
             atomicAdd(&p.dw[idx], __uint_as_float(v[k]));
           }
@@ -611,8 +616,9 @@ struct WPlan {
   size_t smem_bytes = 0;
 };
 
-WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
+WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, bool khs = false) {
   WPlan pl;
+  if (khs && KH != 3) return pl;
   if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
   const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
@@ -624,7 +630,8 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   for (int c = cu_max; c >= 16; c -= 16)
     if (Cin % c == 0) { CU = c; break; }
   int NB = 0;
-  for (int c = (KS == 1 ? 256 : 48); c >= 16; c -= 16)   // KS*KS accumulators of NB columns must fit 512 TMEM columns
+  const int hwr = khs ? 0 : hw;                           // kh-split: the slab starts at the CTA's kernel row, no row halo
+  for (int c = (KS == 1 ? 256 : (khs ? 128 : 48)); c >= 16; c -= 16)   // accumulators (KS*KS, or KS with kh-split) x NB columns must fit 512 TMEM columns
     if (Cout % c == 0) { NB = c; break; }
   if (!CU || !NB) return pl;
   const int chunks_u = CU / 8, chunks_v = NB / 8;
@@ -637,7 +644,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
     if (wb % 16 || W % wb) continue;
     const int pw = wb + 2 * hw;
     for (int R = 1; R <= H + 1 && R <= 32; ++R) {
-      const int RB = R + 2 * hw;
+      const int RB = R + 2 * hwr;
       if (((CU / 16) * RB * pw) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
       size_t a = (size_t)KD * chunks_u * RB * pw * 16;
       size_t b = (size_t)chunks_v * R * wb * 16;
@@ -653,18 +660,18 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   if (!bestR) return pl;
   WParams& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
-  p.out_mode = 0; p.up_cout = 0; p.taps_out = 0;
-  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hw; p.CU = CU; p.NB = NB; p.chunks_u = chunks_u; p.chunks_v = chunks_v;
+  p.out_mode = 0; p.up_cout = 0; p.taps_out = 0; p.khs = khs ? 1 : 0;
+  p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hwr; p.CU = CU; p.NB = NB; p.chunks_u = chunks_u; p.chunks_v = chunks_v;
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_cb = Cin / CU; p.n_nb = Cout / NB;
   p.plane_bytes = (uint32_t)chunks_u * p.RB * PW * 16u;
   p.a_bytes = (uint32_t)KD * p.plane_bytes;
   p.b_bytes = (uint32_t)chunks_v * bestR * WB * 16u;
   p.stage_bytes = (uint32_t)(((size_t)p.a_bytes + p.b_bytes + 1023) & ~(size_t)1023);
   uint32_t cols = 32;
-  while (cols < (uint32_t)(KS * KS * NB)) cols <<= 1;
+  while (cols < (uint32_t)((khs ? KS : KS * KS) * NB)) cols <<= 1;
   p.tmem_cols = cols;
   p.n_pos_items = (long long)N * D * p.n_rb * p.n_wb;
-  const int pairs = p.n_cb * p.n_nb;
+  const int pairs = p.n_cb * p.n_nb * (khs ? 3 : 1);
   long long splits = ich_num_sms() / pairs;      // ONE wave: splits * pairs <= #SMs (a partial second wave would double the time)
   if (splits > p.n_pos_items) splits = p.n_pos_items;
   if (splits < 1) splits = 1;
@@ -722,7 +729,7 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
     ICH_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((unsigned)p.splits, (unsigned)(p.n_cb * p.n_nb));
+  dim3 grid((unsigned)p.splits, (unsigned)(p.n_cb * p.n_nb * (p.khs ? 3 : 1)));
   if (p.KS == 3) conv_tc_wgrad_kernel<3><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
   else conv_tc_wgrad_kernel<1><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
   return ich_check_launch(what);
@@ -730,9 +737,28 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
 
 int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int KD, int KH,
                       int KW, void* stream) {
+  // An MN-major MMA costs ~110 cycles whatever N <= 128 is, and 9 accumulators cap N at 48.  Two ways to put more work in an MMA:
+  //   kh-split : each CTA accumulates ONE kernel row (3 accumulators) -> N up to 128 (used when Cout is a multiple of 64);
+  //   swap     : when only Cin is wide (64 -> 32 layers) the gradient of the transposed problem is computed (U = dy, V = x)
+  //              and written back transposed with flipped taps.
+  static int mode_env = -1;
+  if (mode_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KHS"); mode_env = e ? atoi(e) : 1; }
+  const size_t n_dw = (size_t)Cout * Cin * KD * KH * KW;
+  if (mode_env && KH == 3) {
+    if (Cout % 64 == 0) {
+      WPlan pk = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW, true);
+      if (pk.ok) return launch_conv_tc_wgrad(pk, x, x_ld, dy, dy_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<khs>");
+    } else if (Cin % 64 == 0) {
+      WPlan pk = make_wplan(N, D, H, W, Cout, Cin, KD, KH, KW, true);
+      if (pk.ok) {
+        pk.p.out_mode = 2;
+        return launch_conv_tc_wgrad(pk, dy, dy_ld, x, x_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<khs,swap>");
+      }
+    }
+  }
   WPlan pl = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW);
   ICH_REQUIRE(pl.ok, "ich_conv_tc_wgrad: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
-  return launch_conv_tc_wgrad(pl, x, x_ld, dy, dy_ld, dw, (size_t)Cout * Cin * KD * KH * KW, (cudaStream_t)stream, "ich_conv_tc_wgrad");
+  return launch_conv_tc_wgrad(pl, x, x_ld, dy, dy_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad");
 }
 
 // Transposed conv k2 s2 weight gradient: g = the up-sampled gradient re-packed to the coarse grid by ich_space_to_depth2

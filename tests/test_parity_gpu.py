@@ -390,6 +390,8 @@ TC_CASES = [  # N, D, H, W, Cin, Cout, k3d  -- shapes the tcgen05 kernel must ta
     (1, 5, 10, 24, 48, 48, True),       # odd sizes: W = 24, 48 channels (NB = 48)
     (1, 20, 8, 32, 32, 128, True),      # plane-streaming kernel: 2 depth segments (16 + 4 planes), 2 cout blocks
     (2, 18, 4, 128, 16, 16, True),      # plane-streaming kernel, row mode, NB = 16, ring wraps many times
+    (2, 1, 32, 64, 32, 64, False),      # 2-D, wgrad in kh-split mode (Cout multiple of 64)
+    (1, 4, 16, 128, 64, 32, True),      # wgrad with swapped operands (wide Cin, narrow Cout), w-blocked slab
 ]
 
 
