@@ -89,8 +89,9 @@ int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const flo
 
 /* ---- nn.MaxPool3d/2d(2,2) (models/networks/UNet.py:82,109); grid args = the INPUT grid ------------------------------ */
 int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
+/* dskip (optional): gradient of the SAME tensor arriving through the skip connection (UNet.py:107,119), added in the same pass */
 int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W, int C,
-                     int FD, void* stream);
+                     int FD, const void* dskip, int dskip_ld, void* stream);
 
 /* ---- torch.cat([res, x], 1) (models/networks/UNet.py:119) as channel-slab copies; AdaptiveAvgPool(1) (:295,318) ------ */
 int ich_slab_copy(const void* src, int src_ld, void* dst, int dst_ld, int dtype, long long M, int C, void* stream);

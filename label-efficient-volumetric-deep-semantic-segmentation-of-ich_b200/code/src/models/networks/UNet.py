@@ -173,8 +173,11 @@ class _UNetBase(nn.Module):
             concat_c = ups[j].out_channels if (_cfg.get('zero_copy_concat') and j < len(ups)
                                                and isinstance(ups[j], (nn.ConvTranspose3d, nn.ConvTranspose2d))) else 0
             x = block.forward_cl(x, concat_c)
-            res.append(x)
-            x = ops.MaxPool2.apply(x, self._fd)
+            buf = getattr(x, '_ich_concat_buf', None)
+            skip, x = ops.PoolSkip.apply(x, self._fd)       # skip tensor + pooled tensor; their gradients meet in one kernel
+            if buf is not None:
+                skip._ich_concat_buf = buf
+            res.append(skip)
         return self.bottleneck_block.forward_cl(x), res     # UNet.py:112
 
     def _decode(self, x, res):

@@ -455,7 +455,8 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
 }
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ x, int x_ld, const T* __restrict__ dy, int dy_ld,
-                                                          T* __restrict__ dx, int dx_ld, int N, int D, int H, int W, int C, int FD) {
+                                                          T* __restrict__ dx, int dx_ld, int N, int D, int H, int W, int C, int FD,
+                                                          const T* __restrict__ dskip, int ds_ld) {
   constexpr int V = VEC ? Vec<T>::N : 1;
   const int groups = C / V, Do = D / FD, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Do * Ho * Wo * groups;
@@ -486,6 +487,12 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T* __restrict__ 
           float v[V];
 #pragma unroll
           for (int k = 0; k < V; ++k) v[k] = (arg[k] == ((a << 2) | (b << 1) | e)) ? g[k] : 0.f;
+          if (dskip) {   // the pooled tensor is also a skip connection: add the gradient arriving through the decoder (fp32 add, one rounding)
+            float sk[V];
+            if (VEC) Vec<T>::load(dskip + row * ds_ld + c, sk); else sk[0] = to_f32(dskip[row * ds_ld + c]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) v[k] += sk[k];
+          }
           if (VEC) Vec<T>::store(dx + row * dx_ld + c, v); else dx[row * dx_ld + c] = from_f32<T>(v[0]);
         }
   }
@@ -664,16 +671,16 @@ int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int 
 }
 
 int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W,
-                     int C, int FD, void* stream) {
+                     int C, int FD, const void* dskip, int dskip_ld, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   ICH_REQUIRE((FD == 1 || FD == 2) && D % FD == 0 && H % 2 == 0 && W % 2 == 0, "ich_maxpool2_bwd: grid %dx%dx%d not divisible by the pool", D, H, W);
   long long outv = (long long)N * (D / FD) * (H / 2) * (W / 2);
   if (outv * C == 0) return 0;
   DISPATCH_T(dtype, "ich_maxpool2_bwd", {
-    if (vec_ok<T>(x, x_ld, C) && vec_ok<T>(dy, dy_ld, C) && vec_ok<T>(dx, dx_ld, C))
-      maxpool_bwd_kernel<T, true><<<grid_for(outv * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)x, x_ld, (const T*)dy, dy_ld, (T*)dx, dx_ld, N, D, H, W, C, FD);
+    if (vec_ok<T>(x, x_ld, C) && vec_ok<T>(dy, dy_ld, C) && vec_ok<T>(dx, dx_ld, C) && (!dskip || vec_ok<T>(dskip, dskip_ld, C)))
+      maxpool_bwd_kernel<T, true><<<grid_for(outv * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)x, x_ld, (const T*)dy, dy_ld, (T*)dx, dx_ld, N, D, H, W, C, FD, (const T*)dskip, dskip_ld);
     else
-      maxpool_bwd_kernel<T, false><<<grid_for(outv * C, 256), 256, 0, s>>>((const T*)x, x_ld, (const T*)dy, dy_ld, (T*)dx, dx_ld, N, D, H, W, C, FD);
+      maxpool_bwd_kernel<T, false><<<grid_for(outv * C, 256), 256, 0, s>>>((const T*)x, x_ld, (const T*)dy, dy_ld, (T*)dx, dx_ld, N, D, H, W, C, FD, (const T*)dskip, dskip_ld);
   })
   return ich_check_launch("ich_maxpool2_bwd");
 }

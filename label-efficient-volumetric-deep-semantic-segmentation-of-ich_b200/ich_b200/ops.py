@@ -409,7 +409,43 @@ class MaxPool2(Function):
         dy = dy.contiguous()
         dx = torch.empty((n, d, h, w, c), dtype=x.dtype, device=x.device)
         xp, xld = _rows(x)
-        call('ich_maxpool2_bwd', xp, xld, dy.data_ptr(), c, dx.data_ptr(), c, _dt(x), n, d, h, w, c, ctx.fd, _stream())
+        call('ich_maxpool2_bwd', xp, xld, dy.data_ptr(), c, dx.data_ptr(), c, _dt(x), n, d, h, w, c, ctx.fd, None, 0, _stream())
+        return dx, None
+
+
+class PoolSkip(Function):
+    """Encoder step of UNet.forward (UNet.py:107-109): the block output is kept as the skip tensor AND max-pooled. One Function
+    with two outputs, so that the two gradients of the same tensor (through the decoder concat and through the pooled path)
+    are combined inside the max-pool backward kernel instead of a separate autograd add."""
+
+    @staticmethod
+    def forward(ctx, x, fd):
+        n, d, h, w, c = x.shape
+        y = torch.empty((n, d // fd, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+        xp, xld = _rows(x)
+        call('ich_maxpool2_fwd', xp, xld, y.data_ptr(), c, _dt(x), n, d, h, w, c, fd, _stream())
+        ctx.save_for_backward(x)
+        ctx.fd = fd
+        skip = _alias(x, tuple(x.shape), x.stride())     # same storage, fresh tensor object
+        return skip, y
+
+    @staticmethod
+    def backward(ctx, dskip, dy):
+        (x,) = ctx.saved_tensors
+        n, d, h, w, c = x.shape
+        if dy is None:
+            return (dskip.contiguous() if dskip is not None else None), None
+        dy = dy.contiguous()
+        dx = torch.empty((n, d, h, w, c), dtype=x.dtype, device=x.device)
+        xp, xld = _rows(x)
+        sp, sld = (None, 0)
+        if dskip is not None:
+            try:
+                sp, sld = _rows(dskip)
+            except RuntimeError:
+                dskip = dskip.contiguous()
+                sp, sld = dskip.data_ptr(), c
+        call('ich_maxpool2_bwd', xp, xld, dy.data_ptr(), c, dx.data_ptr(), c, _dt(x), n, d, h, w, c, ctx.fd, sp, sld, _stream())
         return dx, None
 
 
