@@ -183,17 +183,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int f = (p.row_mode ? tt * p.PW : tt * 128) + l;
         const int r = f / p.PW, pos = f - r * p.PW;
         const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W);
-        long long vox;
+        const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
+        bf16* yrow = p.y + vox * p.y_ld + n0;
         int bias0 = n0;
-        if (p.up_fd) {   // transposed conv k2 s2: this cout block belongs to one tap (i, j, l) -> scatter to the fine grid
-          const int tap = n0 / p.up_cout;
-          bias0 = n0 - tap * p.up_cout;
-          const int ti = tap >> 2, tj = (tap >> 1) & 1, tl = tap & 1;
-          vox = ((((long long)n * p.D + d) * p.up_fd + ti) * (2 * p.H) + (2 * (h0 + r) + tj)) * (2 * p.W) + (2 * (w0 + pos) + tl);
-        } else {
-          vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
-        }
-        bf16* yrow = p.y + vox * p.y_ld + bias0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
 #pragma unroll
         for (int c0 = 0; c0 < (KS == 1 ? 256 : 64); c0 += 16) {
@@ -201,6 +193,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
             tmem_ld_wait();
+            if (p.up_fd) {   // transposed conv k2 s2: this 16-column chunk belongs to one tap (i, j, l) -> scatter to the fine grid
+              const int col = n0 + c0;
+              const int tap = col / p.up_cout;
+              bias0 = col - tap * p.up_cout - c0;
+              const int ti = tap >> 2, tj = (tap >> 1) & 1, tl = tap & 1;
+              const long long fine = ((((long long)n * p.D + d) * p.up_fd + ti) * (2 * p.H) + (2 * (h0 + r) + tj)) * (2 * p.W) + (2 * (w0 + pos) + tl);
+              yrow = p.y + fine * p.y_ld + bias0;
+            }
             if (valid && !(p.dbg & 4)) {
               float f32[16];
 #pragma unroll
@@ -431,13 +431,13 @@ int ich_conv_tc_fwd_stats(const void* x, int x_ld, const void* wpack_bf16, void*
 // wpack_bf16 = [taps*Cout][Cin] bf16 (row n = tap*Cout + co), taps = 4*FD.  Grid args = the COARSE grid.
 int ich_convT2_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int FD) {
   if (!get_encode() || (FD != 1 && FD != 2) || Cout % 16) return 0;
-  return make_plan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1, Cout).ok ? 1 : 0;
+  return make_plan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1).ok ? 1 : 0;
 }
 
 int ich_convT2_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W, int Cin,
                       int Cout, int FD, void* stream) {
   ICH_REQUIRE((FD == 1 || FD == 2) && Cout % 16 == 0, "ich_convT2_tc_fwd: unsupported FD %d / Cout %d", FD, Cout);
-  Plan pl = make_plan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1, Cout);
+  Plan pl = make_plan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1);
   ICH_REQUIRE(pl.ok, "ich_convT2_tc_fwd: unsupported shape N%d D%d H%d W%d Cin%d Cout%d", N, D, H, W, Cin, Cout);
   pl.p.up_fd = FD;
   pl.p.up_cout = Cout;
