@@ -29,6 +29,11 @@ int ich_abi_version(void);
 int ich_layout_nc_to_nl(const float* src, void* dst, int dtype, int N, int C, long long S, int dst_ld, void* stream);
 int ich_layout_nl_to_nc(const void* src, int dtype, int src_ld, float* dst, int N, int C, long long S, void* stream);
 
+/* ---- weight packing (derived caches of the fp32 parameters): dst = permute(flip(src)) of a 5-D tensor [d0..d4], dst dim k runs over
+ *      source dim p_k, source dims whose bit is set in flipmask are reversed; dst dtype fp32 or bf16.                                  */
+int ich_permute5(const float* src, void* dst, int dtype, int d0, int d1, int d2, int d3, int d4, int p0, int p1, int p2, int p3, int p4,
+                 int flipmask, void* stream);
+
 /* ---- convolution, "same" padding, stride 1: nn.Conv3d/Conv2d k3 p1 (models/networks/UNet.py:153,155,158,160) and the 1x1
  *      heads (:84, :228).  wpack = [taps*Cin][Cout] fp32.  The data-gradient is the same entry point called with the
  *      flipped/transposed pack.  CUDA-core fp32-accumulate path (fp32 verification mode + odd shapes).               */

@@ -534,6 +534,27 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const T* __restrict
   }
 }
 
+
+// ---- weight packing: dst = permute(flip(src)) of a 5-D fp32 tensor, cast to the destination type, one launch ---------------------
+struct Perm5 { int dims[5]; int perm[5]; int flip; };
+template <typename T>
+__global__ void __launch_bounds__(256) permute5_kernel(const float* __restrict__ src, T* __restrict__ dst, Perm5 q, long long total) {
+  long long sstride[5];
+  sstride[4] = 1;
+  for (int i = 3; i >= 0; --i) sstride[i] = sstride[i + 1] * q.dims[i + 1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i, off = 0;
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {             // destination dim k iterates source dim perm[k]
+      const int sd = q.perm[k], n = q.dims[sd];
+      int idx = (int)(t % n); t /= n;
+      if ((q.flip >> sd) & 1) idx = n - 1 - idx;
+      off += idx * sstride[sd];
+    }
+    dst[i] = from_f32<T>(src[off]);
+  }
+}
+
 // ---- global average pool over the voxels of each sample: x [N][S][C] -> out fp32 [N][C]; and its backward -----------
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ x, int ld, float* __restrict__ out, long long S, int C) {
@@ -709,6 +730,19 @@ int ich_space_to_depth2(const void* src, int src_ld, void* dst, int dtype, int N
       space_to_depth_kernel<T, false><<<grid_for(total, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, N, D, H, W, C, FD);
   })
   return ich_check_launch("ich_space_to_depth2");
+}
+
+int ich_permute5(const float* src, void* dst, int dtype, int d0, int d1, int d2, int d3, int d4, int p0, int p1, int p2, int p3, int p4,
+                 int flipmask, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  Perm5 q{{d0, d1, d2, d3, d4}, {p0, p1, p2, p3, p4}, flipmask};
+  int seen = 0;
+  for (int k = 0; k < 5; ++k) { ICH_REQUIRE(q.perm[k] >= 0 && q.perm[k] < 5, "ich_permute5: bad permutation"); seen |= 1 << q.perm[k]; }
+  ICH_REQUIRE(seen == 31, "ich_permute5: bad permutation");
+  long long total = (long long)d0 * d1 * d2 * d3 * d4;
+  if (total == 0) return 0;
+  DISPATCH_T(dtype, "ich_permute5", { permute5_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(src, (T*)dst, q, total); })
+  return ich_check_launch("ich_permute5");
 }
 
 int ich_avgpool_fwd(const void* x, int ld, int dtype, float* out, int N, long long S, int C, void* stream) {

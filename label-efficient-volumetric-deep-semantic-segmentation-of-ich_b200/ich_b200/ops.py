@@ -72,30 +72,29 @@ def _pack(param, kind):
         param._ich_packs = cache
     packs = cache[1]
     if kind not in packs:
-        with torch.no_grad():
-            w = _as5d(param.detach())
-            if kind == 'conv_fwd':        # [taps*Cin][Cout] fp32
-                packs[kind] = w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).float().contiguous()
-            elif kind == 'conv_dgrad':    # [taps'*Cout][Cin] fp32, taps flipped
-                packs[kind] = w.flip(2, 3, 4).permute(2, 3, 4, 0, 1).reshape(-1, w.shape[1]).float().contiguous()
-            elif kind == 'conv_fwd_tc':   # [taps][Cout][Cin] bf16
-                packs[kind] = w.permute(2, 3, 4, 0, 1).reshape(-1, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
-            elif kind == 'conv_dgrad_tc':  # [taps'][Cin][Cout] bf16
-                packs[kind] = w.flip(2, 3, 4).permute(2, 3, 4, 1, 0).reshape(-1, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
-            elif kind == 'conv_fwd_tc_s':   # plane-streaming kernel: [kh][kw][2-kd][Cout][Cin] bf16
-                packs[kind] = w.flip(2).permute(3, 4, 2, 0, 1).reshape(-1, w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
-            elif kind == 'conv_dgrad_tc_s':  # same for the data-gradient conv (taps flipped, channels transposed)
-                packs[kind] = w.flip(3, 4).permute(3, 4, 2, 1, 0).reshape(-1, w.shape[1], w.shape[0]).to(torch.bfloat16).contiguous()
-            elif kind == 'convT_fwd_tc':  # [taps*Cout][Cin] bf16 (B operand of the up-sampling GEMM)
-                packs[kind] = w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).to(torch.bfloat16).contiguous()
-            elif kind == 'convT_dgrad_tc':  # [Cin][taps*Cout] bf16 (B operand of the 1x1 data-gradient GEMM)
-                packs[kind] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
-            elif kind == 'convT_fwd':     # [Cin][taps*Cout] fp32
-                packs[kind] = w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).float().contiguous()
-            elif kind == 'convT_dgrad':   # [taps*Cout][Cin] fp32
-                packs[kind] = w.permute(2, 3, 4, 1, 0).reshape(-1, w.shape[0]).float().contiguous()
-            else:
-                raise KeyError(kind)
+        # source dims: conv [co, ci, kd, kh, kw]; transposed conv [ci, co, i, j, l].  (perm, flipped source dims, bf16?, final shape)
+        w = _as5d(param.detach())
+        a, b = w.shape[0], w.shape[1]
+        taps = w.shape[2] * w.shape[3] * w.shape[4]
+        spec = {
+            'conv_fwd':        ((2, 3, 4, 1, 0), (),        False, (taps * b, a)),      # [taps*Cin][Cout] fp32
+            'conv_dgrad':      ((2, 3, 4, 0, 1), (2, 3, 4), False, (taps * a, b)),      # [taps'*Cout][Cin] fp32, taps flipped
+            'conv_fwd_tc':     ((2, 3, 4, 0, 1), (),        True,  (taps, a, b)),       # [taps][Cout][Cin] bf16
+            'conv_dgrad_tc':   ((2, 3, 4, 1, 0), (2, 3, 4), True,  (taps, b, a)),       # [taps'][Cin][Cout] bf16
+            'conv_fwd_tc_s':   ((3, 4, 2, 0, 1), (2,),      True,  (taps, a, b)),       # plane-streaming kernel: [kh][kw][2-kd][Cout][Cin] bf16
+            'conv_dgrad_tc_s': ((3, 4, 2, 1, 0), (3, 4),    True,  (taps, b, a)),       # same for the data-gradient conv
+            'convT_fwd_tc':    ((2, 3, 4, 1, 0), (),        True,  (taps * b, a)),      # [taps*Cout][Cin] bf16
+            'convT_dgrad_tc':  ((0, 2, 3, 4, 1), (),        True,  (a, taps * b)),      # [Cin][taps*Cout] bf16
+            'convT_fwd':       ((0, 2, 3, 4, 1), (),        False, (a, taps * b)),      # [Cin][taps*Cout] fp32
+            'convT_dgrad':     ((2, 3, 4, 1, 0), (),        False, (taps * b, a)),      # [taps*Cout][Cin] fp32
+        }
+        if kind not in spec:
+            raise KeyError(kind)
+        perm, flips, bf16, shape = spec[kind]
+        src = w.float().contiguous()
+        dst = torch.empty(shape, dtype=torch.bfloat16 if bf16 else torch.float32, device=w.device)
+        call('ich_permute5', src.data_ptr(), dst.data_ptr(), 1 if bf16 else 0, *w.shape, *perm, sum(1 << f for f in flips), _stream())
+        packs[kind] = dst
     return packs[kind]
 
 
