@@ -24,7 +24,8 @@ struct SParams {
   int n_wb, n_rb, n_nb, KC;
   int DS, n_ds;
   int stages;
-  uint32_t a_bytes, a_tx_bytes, b_bytes, stage_bytes, tmem_cols;
+  int b_resident;            // 1: the weights of ALL channel chunks stay in shared memory for the CTA's lifetime (stage = slab only)
+  uint32_t a_bytes, a_tx_bytes, b_bytes, stage_bytes, w_offset, tmem_cols;
   long long n_items;
   bf16* y;
   int y_ld;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
 conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const SParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[S_MAX_STAGES], empty_bar[S_MAX_STAGES], tfull_bar[SLOTS], tempty_bar[SLOTS];
+  __shared__ __align__(8) uint64_t full_bar[S_MAX_STAGES], empty_bar[S_MAX_STAGES], tfull_bar[SLOTS], tempty_bar[SLOTS], w_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -60,6 +61,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < SLOTS; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -81,6 +83,14 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 
   if (warp == 0) {
     // ===================================================== TMA producer
+    if (p.b_resident && s_begin < n_spatial) {   // all channel chunks of this CTA's weight block, once (they are re-read 100s of times otherwise,
+      if (elect_one()) {                         // by every CTA at the same moment: hot L2 lines, address-dependent slowdowns were measured)
+        mbar_expect_tx(&w_bar, p.b_bytes * (uint32_t)p.KC);
+        for (int kc = 0; kc < p.KC; ++kc)
+          tma_load_3d(smem + p.w_offset + (size_t)kc * p.b_bytes, &map_w, &w_bar, kc * 16, nb_fixed * p.NB, 0);
+      }
+      __syncwarp();
+    }
     int stage = 0; uint32_t phase = 0;
     for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
       long long t = sp;
@@ -96,9 +106,9 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_bytes;
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
+            mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + (p.b_resident ? 0u : p.b_bytes));
             tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + pl);
-            tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb_fixed * p.NB, 0);
+            if (!p.b_resident) tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb_fixed * p.NB, 0);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -116,6 +126,8 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     const int T = p.T;
     int stage = 0; uint32_t phase = 0;
     long long g_base = 0;                                              // output planes completed by this CTA so far
+    if (p.b_resident && s_begin < n_spatial) { mbar_wait(&w_bar, 0); tc_fence_after(); }
+    const uint32_t w_base = smem_u32(smem + p.w_offset);
     for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
       long long t = sp / p.n_wb / p.n_rb;
       const int ds = (int)(t % p.n_ds);
@@ -135,7 +147,8 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
             const uint32_t a_lo0 = ((sa & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t b_lo0 = (((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_addr = p.b_resident ? (w_base + (uint32_t)kc * p.b_bytes) : (sa + p.a_bytes);
+            const uint32_t b_lo0 = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
             uint32_t a_kh = a_lo0;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
@@ -284,7 +297,7 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
   const bool row_mode = (WB == 128);
   const int Tmax = 512 / (SLOTS * NB);
   const uint32_t b_bytes = 27u * NB * 32u;
-  int bestR = 0, bestT = 0, bestStages = 0;
+  int bestR = 0, bestT = 0, bestStages = 0, bestRes = 0;
   size_t best_smem = 0;
   uint32_t best_a = 0;
   long long best_cost = -1;
@@ -296,15 +309,23 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
     a_bytes = (a_bytes + 127u) & ~127u;
     long long over = row_mode ? 0 : ((long long)(128 * T + 2 * PW + 2) - (long long)RB * PW) * 32;
     if (over < 0) over = 0;
-    size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
-    int stages = (int)((SMEM_LIMIT - (size_t)over - 1024) / stage);
+    // resident weights (all Cin/16 chunks) when they leave room for >= 3 slab stages, else weights travel with every stage
+    const size_t w_all = (size_t)b_bytes * (Cin / 16);
+    size_t stage = ((size_t)a_bytes + 1023) & ~(size_t)1023;
+    int resident = 1;
+    int stages = (SMEM_LIMIT > w_all + (size_t)over + 2048) ? (int)((SMEM_LIMIT - w_all - (size_t)over - 2048) / stage) : 0;
+    if (stages < 3) {
+      resident = 0;
+      stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
+      stages = (int)((SMEM_LIMIT - (size_t)over - 1024) / stage);
+    }
     if (stages > S_MAX_STAGES) stages = S_MAX_STAGES;
     if (stages < 2) continue;
-    size_t total = (size_t)stages * stage + (size_t)over + 1024;
+    size_t total = (size_t)stages * stage + (resident ? w_all + 1024 : 0) + (size_t)over + 1024;
     long long blocks = (H + R - 1) / R;
     long long cost = blocks * T * 1000 + blocks * RB * 30;
     if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost; bestR = R; bestT = T; bestStages = stages; best_smem = total; best_a = a_bytes;
+      best_cost = cost; bestR = R; bestT = T; bestStages = stages; best_smem = total; best_a = a_bytes; bestRes = resident;
     }
   }
   if (best_cost < 0) return pl;
@@ -318,7 +339,9 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
   p.a_bytes = best_a;
   p.a_tx_bytes = (uint32_t)p.RB * PW * 32u;     // bytes the TMA box really delivers (a_bytes is rounded up for alignment)
   p.b_bytes = b_bytes;
-  p.stage_bytes = (uint32_t)(((size_t)best_a + b_bytes + 1023) & ~(size_t)1023);
+  p.b_resident = bestRes;
+  p.stage_bytes = (uint32_t)(((size_t)best_a + (bestRes ? 0 : b_bytes) + 1023) & ~(size_t)1023);
+  p.w_offset = (uint32_t)((size_t)bestStages * p.stage_bytes);   // resident weights sit after the slab stages (1024-byte aligned)
   uint32_t cols = 32;
   while (cols < (uint32_t)(SLOTS * bestT * NB)) cols <<= 1;
   p.tmem_cols = cols;
