@@ -55,6 +55,15 @@ int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float
 /* same, with the BatchNorm batch statistics (fp64 per-channel sum / sum of squares of the stored outputs) fused into the epilogue */
 int ich_conv_tc_fwd_stats(const void* x, int x_ld, const void* wpack_bf16, void* y, int y_ld, double* sum, double* sumsq, int N, int D,
                           int H, int W, int Cin, int Cout, int KD, int KH, int KW, void* stream);
+/* first layer (Cin = 1, the CT intensity: UNet.py:153 with in_channels = 1) on tcgen05: the 27-tap (2-D: 9-tap) im2col row of a
+ * voxel is built in shared memory (K padded to 32), bf16 x bf16 -> fp32.  HBM-bound.  wpack = [taps][Cout] fp32 (the
+ * ich_conv_fwd pack).  sum / sumsq (both or neither): fused BatchNorm batch statistics of the stored outputs, zeroed here.
+ * Requires Cout in {8, 16, 24, 32}.  dw in torch layout [Cout][1][taps] fp32.                                             */
+int ich_conv_cin1_tc_supported(int N, int D, int H, int W, int Cout, int KD);
+int ich_conv_cin1_tc_fwd(const void* x, int x_ld, const float* wpack, const float* bias, void* y, int y_ld, double* sum, double* sumsq, int N,
+                         int D, int H, int W, int Cout, int KD, int relu, void* stream);
+int ich_conv_cin1_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float* dw, int N, int D, int H, int W, int Cout, int KD,
+                           void* stream);
 /* transposed conv k2 s2 on tensor cores (same call site as ich_convT2_fwd): 1x1 GEMM + depth-to-space scatter epilogue.
  * wpack_bf16 = [taps*Cout][Cin] bf16.  Grid args = the COARSE grid.                                                   */
 int ich_convT2_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int FD);

@@ -756,6 +756,17 @@ int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float*
       }
     }
   }
+  // narrow-Cin layers (16 -> 32): with rows = (kd, ci) only 48 of the 128 MMA rows are live; the transposed problem has
+  // rows = (kd, co) = 96 live rows and N = Cin = 16 columns per accumulator (cheaper MMAs, same count)
+  static int swap16_env = -1;
+  if (swap16_env < 0) { const char* e = getenv("ICH_TC_WGRAD_SWAP16"); swap16_env = e ? atoi(e) : 1; }
+  if (swap16_env && KH == 3 && KD == 3 && Cin == 16 && Cout % 32 == 0) {
+    WPlan ps = make_wplan(N, D, H, W, Cout, Cin, KD, KH, KW);
+    if (ps.ok) {
+      ps.p.out_mode = 2;
+      return launch_conv_tc_wgrad(ps, dy, dy_ld, x, x_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<swap>");
+    }
+  }
   WPlan pl = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW);
   ICH_REQUIRE(pl.ok, "ich_conv_tc_wgrad: unsupported shape N%d D%d H%d W%d Cin%d Cout%d k%dx%dx%d", N, D, H, W, Cin, Cout, KD, KH, KW);
   return launch_conv_tc_wgrad(pl, x, x_ld, dy, dy_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad");

@@ -116,6 +116,15 @@ def _use_tc(x, cin, cout, k):
     return _tc_variant(x, cin, cout, k) != 0
 
 
+def _cin1_tc(x, cin, cout, k):
+    """First layer (Cin = 1) on the tcgen05 im2col kernels (bf16 engine only)."""
+    if cin != 1 or k[1] != 3 or k[2] != 3 or not (config.get('tensor_cores') and x.dtype == torch.bfloat16):
+        return False
+    from ._lib import lib
+    n, d, h, w, _ = x.shape
+    return bool(lib().ich_conv_cin1_tc_supported(n, d, h, w, cout, k[0]))
+
+
 # bench.py sets PROFILE = [] to collect (kind, flops, start_event, end_event) per conv kernel launch
 PROFILE = None
 
@@ -157,6 +166,9 @@ def _conv_forward(x, weight, bias, relu):
     if var:
         call('ich_conv_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd_tc_s' if var == 2 else 'conv_fwd_tc')), _p(bias), y.data_ptr(), cout,
              n, d, h, w, cin, cout, *k, int(relu), _stream())
+    elif _cin1_tc(x, cin, cout, k):
+        call('ich_conv_cin1_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd')), _p(bias), y.data_ptr(), cout, None, None, n, d, h, w, cout, k[0],
+             int(relu), _stream())
     else:
         call('ich_conv_fwd', xp, xld, _p(_pack(weight, 'conv_fwd')), _p(bias), y.data_ptr(), cout, _dt(x), n, d, h, w, cin, cout, *k,
              int(relu), _stream())
@@ -204,6 +216,8 @@ def _conv_wgrad(x, dy, weight):
     from ._lib import lib
     if config.get('tensor_cores') and x.dtype == torch.bfloat16 and lib().ich_conv_tc_wgrad_supported(n, d, h, w, cin, cout, *k):
         call('ich_conv_tc_wgrad', xp, xld, yp, yld, dw.data_ptr(), n, d, h, w, cin, cout, *k, _stream())
+    elif _cin1_tc(x, cin, cout, k) and yld % 8 == 0:
+        call('ich_conv_cin1_tc_wgrad', xp, xld, yp, yld, dw.data_ptr(), n, d, h, w, cout, k[0], _stream())
     else:
         call('ich_conv_wgrad', xp, xld, yp, yld, _dt(x), dw.data_ptr(), n, d, h, w, cin, cout, *k, _stream())
     return dw
@@ -297,6 +311,13 @@ class ConvBnRelu(Function):
             with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
                 call('ich_conv_tc_fwd_stats', xp, xld, _p(_pack(weight, 'conv_fwd_tc_s' if var == 2 else 'conv_fwd_tc')), y.data_ptr(), cout, sums[0].data_ptr(),
                      sums[1].data_ptr(), n, d, h, w, cin, cout, *k, _stream())
+        elif training and _cin1_tc(x, cin, cout, k):
+            # first layer: tcgen05 im2col kernel, batch statistics fused the same way
+            y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=dev)
+            xp, xld = _rows(x)
+            with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
+                call('ich_conv_cin1_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd')), None, y.data_ptr(), cout, sums[0].data_ptr(), sums[1].data_ptr(),
+                     n, d, h, w, cout, k[0], 0, _stream())
         else:
             y = conv_forward(x, weight, None)
             if training:
