@@ -464,6 +464,10 @@ struct WParams {
   int out_mode, up_cout, taps_out;   // out_mode 1: transposed-conv layout dW[ci][co][tap], columns n = tap*up_cout + co;
                                      // out_mode 2: operands swapped (U = dy, V = x): rows = co, columns = ci, taps flipped
   int khs;                           // kh-split: a CTA handles ONE kernel row kh (3 accumulators -> N up to 128); grid.y = pairs * 3
+  int kwf;                           // kw-fold: the three kw taps are the N dimension (N = 3 * 32): dy lands as 64-byte rows WITH a column halo and
+                                     // MN block j of the B operand is the same tile shifted by j positions (LBO = one row) -> 3 MMAs per K step
+  uint32_t a_off, b_off;             // operand offsets inside a stage
+  int a64;                           // x slab as 64-byte SWIZZLE_64B rows (32-channel blocks) instead of 32-byte rows: half the TMA requests
   int WB, PW, R, RB, CU, NB, chunks_u, chunks_v;
   int n_wb, n_rb, n_cb, n_nb;
   uint32_t plane_bytes, a_bytes, b_bytes, stage_bytes, tmem_cols;
@@ -515,17 +519,18 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int d = (int)(t % p.D); const int n = (int)(t / p.D);
         const int w0 = wb * p.WB, h0 = rb * p.R;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-        uint8_t* sb = sa + p.a_bytes;
+        uint8_t* sa = smem + (size_t)stage * p.stage_bytes + p.a_off;
+        uint8_t* sb = smem + (size_t)stage * p.stage_bytes + p.b_off;
         if (p.dbg & 2) { if (elect_one()) mbar_arrive(&full_bar[stage]); }
         else if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
           for (int pl = 0; pl < p.KD; ++pl) {
             const int dd = d + pl - (p.KD == 3 ? 1 : 0);
             const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
-            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2 + khf, cb * (p.CU / 16), coord);
+            tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2 + khf, cb * (p.CU / (p.a64 ? 32 : 16)), coord);
           }
-          tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / 16), n * p.D + d);
+          if (p.kwf) tma_load_4d(sb, &map_dy, &full_bar[stage], nb * 32, w0 - 1, h0, n * p.D + d);
+          else tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / 16), n * p.D + d);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -534,32 +539,53 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   } else if (warp == 1) {
     {
       // both operands MN-major (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = NB
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((p.kwf ? 3 * p.NB : p.NB) >> 3) << 17) | ((128u >> 4) << 24);
       // MN-major SWIZZLE_32B operands: a position is a 32-byte row of 16 channels; 16-channel blocks are LBO apart (uniform
       // across the planes of the x slab), 8-position groups SBO = 256 B apart.  descriptor = {lo: start>>4 | LBO>>4 << 16,
       // hi: SBO>>4 | version | layout}; per MMA only the start changes (one add + one pack).  All offsets below are in 16-byte units.
       const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);
-      const uint32_t a_lbo = (((uint32_t)p.RB * p.PW * 32u) >> 4) << 16;
+      const uint32_t AU = p.a64 ? 4u : 2u;                                         // 16-byte units per x position
+      const uint32_t a_lbo = (((uint32_t)p.RB * p.PW * 16u * AU) >> 4) << 16;      // channel-block stride (16 or 32 channels per block)
       const uint32_t b_lbo = (((uint32_t)p.R * p.WB * 32u) >> 4) << 16;
-      const uint32_t a_hi = desc_hi, b_hi = desc_hi;
-      const uint32_t PW = 2u * (uint32_t)p.PW, WB = 2u * (uint32_t)p.WB, NB = (uint32_t)p.NB;   // row pitches in 16-byte units
+      const uint32_t a_hi = p.a64 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi, b_hi = desc_hi;
+      const uint32_t PW = AU * (uint32_t)p.PW, WB = 2u * (uint32_t)p.WB, NB = (uint32_t)p.NB;   // row pitches in 16-byte units
       int stage = 0; uint32_t phase = 0;
       uint32_t accum = 0u;
       for (long long item = it_begin; item < it_end; ++item) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t sa = st + p.a_off;
         uint32_t a_row = ((sa & 0x3FFFFu) >> 4) | a_lbo;                           // one position = 32 B = 2 units
-        uint32_t b_row = (((sa + p.a_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+        uint32_t b_row = (((st + p.b_off) & 0x3FFFFu) >> 4) | b_lbo;
+        if (p.kwf) {
+          // B = dy slab [row][WB + 2 positions][32 co] as 64-byte SWIZZLE_64B rows; MN block j (32 columns) = the tile shifted by j
+          // positions (LBO = 64 B), i.e. dy[q + j - 1] for x position q: column block j is kernel column kw = 2 - j.
+          const uint32_t kb_hi = (512u >> 4) | (1u << 14) | (4u << 29);
+          uint32_t bk_row = (((st + p.b_off) & 0x3FFFFu) >> 4) | ((64u >> 4) << 16);
+          const uint32_t BW = 4u * (uint32_t)(p.WB + 2);                           // dy row pitch in 16-byte units
+          for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, bk_row += BW) {
+            for (uint32_t s = 0; s < (uint32_t)p.WB; s += 16) {                    // 16 positions per MMA
+              const uint64_t bdesc = pack64(bk_row + 4u * s, kb_hi);
+              uint32_t a_kh = a_row + AU * s + AU;                                 // x position q = s (skip the halo column)
+              uint32_t dcol = tmem_base;
+              for (int kh = 0; kh < khn; ++kh, a_kh += PW) {
+                if (elect_one()) umma_bf16(dcol, pack64(a_kh, a_hi), bdesc, idesc, accum);
+                dcol += 3u * NB;
+              }
+              accum = 1u;
+            }
+          }
+        } else
         for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, b_row += WB) {
           for (uint32_t s16 = 0; s16 < WB; s16 += 32) {                            // 16 positions per MMA
             const uint64_t bdesc = pack64(b_row + s16, b_hi);
-            uint32_t a_kh = a_row + s16;
+            uint32_t a_kh = a_row + (s16 >> 1) * AU;
             uint32_t dcol = tmem_base;
             for (int kh = 0; kh < khn; ++kh, a_kh += PW) {
 #pragma unroll
               for (int kw = 0; kw < KS; ++kw) {
-                if (elect_one()) umma_bf16(dcol, pack64(a_kh + 2u * (uint32_t)kw, a_hi), bdesc, idesc, accum);
+                if (elect_one()) umma_bf16(dcol, pack64(a_kh + AU * (uint32_t)kw, a_hi), bdesc, idesc, accum);
                 dcol += NB;
               }
             }
@@ -583,7 +609,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     mbar_wait(&done_bar, 0);
     tc_fence_after();
     for (int j = 0; j < khn * KS; ++j) {
-      const int tap = kd * KS * KS + khf * KS + j;
+      const int tap = kd * KS * KS + khf * KS + (p.kwf ? (j / 3) * 3 + 2 - (j % 3) : j);
       for (int c0 = 0; c0 < p.NB; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.NB + c0), v);
@@ -616,9 +642,10 @@ struct WPlan {
   size_t smem_bytes = 0;
 };
 
-WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, bool khs = false) {
+WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, bool khs = false, bool kwf = false) {
   WPlan pl;
   if (khs && KH != 3) return pl;
+  if (kwf && (KH != 3 || khs || Cout % 32)) return pl;
   if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
   const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
@@ -633,6 +660,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   const int hwr = khs ? 0 : hw;                           // kh-split: the slab starts at the CTA's kernel row, no row halo
   for (int c = (KS == 1 ? 256 : (khs ? 128 : 48)); c >= 16; c -= 16)   // accumulators (KS*KS, or KS with kh-split) x NB columns must fit 512 TMEM columns
     if (Cout % c == 0) { NB = c; break; }
+  if (kwf) NB = 32;
   if (!CU || !NB) return pl;
   const int chunks_u = CU / 8, chunks_v = NB / 8;
   // Search the slab shape (w-block WB x R rows): the full-resolution layers are bound by L2->SMEM traffic, so minimise the halo
@@ -647,7 +675,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
       const int RB = R + 2 * hwr;
       if (((CU / 16) * RB * pw) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
       size_t a = (size_t)KD * chunks_u * RB * pw * 16;
-      size_t b = (size_t)chunks_v * R * wb * 16;
+      size_t b = kwf ? (size_t)R * (wb + 2) * 64 : (size_t)chunks_v * R * wb * 16;
       size_t stage = (a + b + 1023) & ~(size_t)1023;
       // the MMA always reads 16 chunks (128 rows): chunks beyond KD*chunks_u are garbage rows, but must stay inside the allocation
       size_t over = (size_t)(16 - KD * chunks_u > 0 ? 16 - KD * chunks_u : 0) * RB * pw * 16 + (size_t)(2 * pw + 32) * 16;
@@ -665,8 +693,14 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_cb = Cin / CU; p.n_nb = Cout / NB;
   p.plane_bytes = (uint32_t)chunks_u * p.RB * PW * 16u;
   p.a_bytes = (uint32_t)KD * p.plane_bytes;
-  p.b_bytes = (uint32_t)chunks_v * bestR * WB * 16u;
+  p.b_bytes = kwf ? (uint32_t)bestR * (WB + 2) * 64u : (uint32_t)chunks_v * bestR * WB * 16u;
   p.stage_bytes = (uint32_t)(((size_t)p.a_bytes + p.b_bytes + 1023) & ~(size_t)1023);
+  p.kwf = kwf ? 1 : 0;
+  { static int a64_env = -1; if (a64_env < 0) { const char* e = getenv("ICH_TC_WGRAD_A64"); a64_env = e ? atoi(e) : 1; }
+    p.a64 = (a64_env && CU % 32 == 0) ? 1 : 0; }
+  // kw-fold: the 64-byte-swizzled dy tile sits at the (1024-byte aligned) stage base, the x planes follow it
+  p.a_off = kwf ? p.b_bytes : 0u;
+  p.b_off = kwf ? 0u : p.a_bytes;
   uint32_t cols = 32;
   while (cols < (uint32_t)((khs ? KS : KS * KS) * NB)) cols <<= 1;
   p.tmem_cols = cols;
@@ -706,14 +740,23 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   {
     // (c16, W, H, C/16, N*D): the box lands as [16-channel block][row][pos][16 ch] = 32-byte swizzled rows (full L2 sectors)
-    cuuint64_t dims[5] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 16), (cuuint64_t)N * D};
-    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, 32, (cuuint64_t)H * W * x_ld * 2};
-    cuuint32_t box[5] = {16, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)(p.CU / 16), 1};
+    const cuuint32_t cbk = p.a64 ? 32 : 16;     // channels per block = one swizzled row
+    cuuint64_t dims[5] = {cbk, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / cbk), (cuuint64_t)N * D};
+    cuuint64_t strides[4] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, 2ull * cbk, (cuuint64_t)H * W * x_ld * 2};
+    cuuint32_t box[5] = {cbk, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)(p.CU / cbk), 1};
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     p.a64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(x) failed with %d", what, (int)r);
   }
-  {
+  if (p.kwf) {
+    // (C, W, H, N*D): the box lands as [row][WB + 2 positions][32 channels] = 64-byte swizzled rows; the column halo is zero-filled
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
+    cuuint64_t strides[3] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, (cuuint64_t)H * W * dy_ld * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)(p.WB + 2), (cuuint32_t)p.R, 1};
+    CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy, kw-fold) failed with %d", what, (int)r);
+  } else {
     cuuint64_t dims[5] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 16), (cuuint64_t)N * D};
     cuuint64_t strides[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, 32, (cuuint64_t)H * W * dy_ld * 2};
     cuuint32_t box[5] = {16, (cuuint32_t)p.WB, (cuuint32_t)p.R, (cuuint32_t)(p.NB / 16), 1};
@@ -741,9 +784,16 @@ int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float*
   //   kh-split : each CTA accumulates ONE kernel row (3 accumulators) -> N up to 128 (used when Cout is a multiple of 64);
   //   swap     : when only Cin is wide (64 -> 32 layers) the gradient of the transposed problem is computed (U = dy, V = x)
   //              and written back transposed with flipped taps.
-  static int mode_env = -1;
+  static int mode_env = -1, kwf_env = -1;
   if (mode_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KHS"); mode_env = e ? atoi(e) : 1; }
+  if (kwf_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KWF"); kwf_env = e ? atoi(e) : 1; }
   const size_t n_dw = (size_t)Cout * Cin * KD * KH * KW;
+  //   kw-fold  : Cout blocks of 32 with the three kw taps folded into N = 96 (an MMA costs 32 + N/4 cycles of operand fetch for
+  //              N <= 128, scratch/mma_rate2.cu: 3 MMAs of 56 cycles replace 9 of 40) -- the narrow-Cout (32 / 64) layers.
+  if (kwf_env && KH == 3 && (Cout == 32 || (Cout == 64 && (kwf_env & 2)))) {
+    WPlan pk = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW, false, true);
+    if (pk.ok) return launch_conv_tc_wgrad(pk, x, x_ld, dy, dy_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<kwf>");
+  }
   if (mode_env && KH == 3) {
     if (Cout % 64 == 0) {
       WPlan pk = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW, true);
