@@ -37,6 +37,8 @@ struct Params {
 constexpr int STAGES = 2;        // weight-gradient kernel
 constexpr int MAX_STAGES = 8;    // forward kernel: runtime depth (2 for the big 3x3 slabs, up to 8 for the small 1x1 GEMM stages)
 constexpr int NUM_THREADS = 192;
+constexpr int W_THREADS = 256;   // weight-gradient kernel: warp 0 TMA, warps 1 / 6 / 7 MMA issuers (one per accumulator group), warps 2..5 epilogue
+constexpr int W_ISSUERS = 3;
 
 template <int KS, bool STATS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -478,7 +480,7 @@ struct WParams {
 };
 
 template <int KS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(W_THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -490,8 +492,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_dy);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&done_bar, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], W_ISSUERS); }
+    mbar_init(&done_bar, W_ISSUERS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -536,8 +538,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp >= 6) {
     {
+      // Three issuer warps (different SM sub-partitions), each owning its own accumulators: the issue loop of ONE warp costs more
+      // cycles per MMA (~70-90, uniform-datapath instruction latency) than the MMA itself (40-56).  Issuer ii takes kernel row
+      // kh = ii (kernel column kw = ii in kh-split mode); the 1x1 GEMMs have a single accumulator (issuer 0).
+      const int ii = warp == 1 ? 0 : warp - 5;
       // both operands MN-major (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = NB
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((p.kwf ? 3 * p.NB : p.NB) >> 3) << 17) | ((128u >> 4) << 24);
       // MN-major SWIZZLE_32B operands: a position is a 32-byte row of 16 channels; 16-channel blocks are LBO apart (uniform
@@ -567,12 +573,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, bk_row += BW) {
             for (uint32_t s = 0; s < (uint32_t)p.WB; s += 16) {                    // 16 positions per MMA
               const uint64_t bdesc = pack64(bk_row + 4u * s, kb_hi);
-              uint32_t a_kh = a_row + AU * s + AU;                                 // x position q = s (skip the halo column)
-              uint32_t dcol = tmem_base;
-              for (int kh = 0; kh < khn; ++kh, a_kh += PW) {
-                if (elect_one()) umma_bf16(dcol, pack64(a_kh, a_hi), bdesc, idesc, accum);
-                dcol += 3u * NB;
-              }
+              const uint32_t a_kh = a_row + AU * s + AU + (uint32_t)ii * PW;       // x position q = s (skip the halo column), kernel row ii
+              if (elect_one()) umma_bf16(tmem_base + (uint32_t)ii * 3u * NB, pack64(a_kh, a_hi), bdesc, idesc, accum);
               accum = 1u;
             }
           }
@@ -580,9 +582,14 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, b_row += WB) {
           for (uint32_t s16 = 0; s16 < WB; s16 += 32) {                            // 16 positions per MMA
             const uint64_t bdesc = pack64(b_row + s16, b_hi);
-            uint32_t a_kh = a_row + (s16 >> 1) * AU;
-            uint32_t dcol = tmem_base;
-            for (int kh = 0; kh < khn; ++kh, a_kh += PW) {
+            const uint32_t a_s = a_row + (s16 >> 1) * AU;
+            if (KS == 1) {                 // 1x1 GEMM: one accumulator
+              if (ii == 0 && elect_one()) umma_bf16(tmem_base, pack64(a_s, a_hi), bdesc, idesc, accum);
+            } else if (khn == 1) {         // kh-split: accumulators = kw, this issuer's is kw = ii
+              if (elect_one()) umma_bf16(tmem_base + (uint32_t)ii * NB, pack64(a_s + AU * (uint32_t)ii, a_hi), bdesc, idesc, accum);
+            } else {                       // 9 accumulators (kh, kw): this issuer's kernel row is kh = ii
+              const uint32_t a_kh = a_s + (uint32_t)ii * PW;
+              uint32_t dcol = tmem_base + (uint32_t)ii * (uint32_t)KS * NB;
 #pragma unroll
               for (int kw = 0; kw < KS; ++kw) {
                 if (elect_one()) umma_bf16(dcol, pack64(a_kh + AU * (uint32_t)kw, a_hi), bdesc, idesc, accum);
@@ -599,7 +606,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       if (elect_one()) umma_commit(&done_bar);
       __syncwarp();
     }
-  } else if (it_begin < it_end) {
+  } else if (warp >= 2 && warp <= 5 && it_begin < it_end) {
     // epilogue: TMEM lane = MMA row m = (kd, ci_local); 9 accumulators of NB columns
     const int q = warp & 3;
     const int m = q * 32 + lane;
@@ -773,8 +780,8 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
     attr_set = true;
   }
   dim3 grid((unsigned)p.splits, (unsigned)(p.n_cb * p.n_nb * (p.khs ? 3 : 1)));
-  if (p.KS == 3) conv_tc_wgrad_kernel<3><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
-  else conv_tc_wgrad_kernel<1><<<grid, NUM_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
+  if (p.KS == 3) conv_tc_wgrad_kernel<3><<<grid, W_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
+  else conv_tc_wgrad_kernel<1><<<grid, W_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
   return ich_check_launch(what);
 }
 

@@ -33,9 +33,11 @@ struct SParams {
   int relu;
   double* stat_sum;
   double* stat_sumsq;
+  int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA slab loads, 4 = no epilogue math / stores
 };
 
-constexpr int S_THREADS = 192;
+constexpr int S_THREADS = 224;      // warp 0: TMA, warps 1 and 6: MMA issuers (even / odd tiles), warps 2..5: epilogue
+constexpr int S_ISSUERS = 2;
 constexpr int S_MAX_STAGES = 6;
 constexpr int SLOTS = 4;
 
@@ -59,8 +61,8 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < SLOTS; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], S_ISSUERS); }
+    for (int a = 0; a < SLOTS; ++a) { mbar_init(&tfull_bar[a], S_ISSUERS); mbar_init(&tempty_bar[a], 4); }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
@@ -69,7 +71,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  if (warp >= 2) {   // all accumulator slots start out zero: every MMA accumulates
+  if (warp >= 2 && warp <= 5) {   // all accumulator slots start out zero: every MMA accumulates
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     for (uint32_t c = 0; c < (uint32_t)(p.T * SLOTS * p.NB); c += 16) tmem_st16_zero(lane_base + c);
     tmem_st_wait();
@@ -106,17 +108,23 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_bytes;
           if (elect_one()) {
-            mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + (p.b_resident ? 0u : p.b_bytes));
-            tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + pl);
-            if (!p.b_resident) tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb_fixed * p.NB, 0);
+            if (p.dbg & 2) mbar_arrive(&full_bar[stage]);
+            else {
+              mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + (p.b_resident ? 0u : p.b_bytes));
+              tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + pl);
+              if (!p.b_resident) tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb_fixed * p.NB, 0);
+            }
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer
+  } else if (warp == 1 || warp == 6) {
+    // ===================================================== MMA issuers.  The issue loop is bound by the latency of its own (uniform
+    // datapath) instruction stream -- ~68 cycles per MMA measured with the MMAs themselves ablated, against 56 cycles of tensor
+    // work for N = 96 -- so TWO warps on different SM sub-partitions issue the even and the odd tiles of every (plane, chunk, tap).
+    const int ii = warp == 1 ? 0 : 1;
     const uint32_t NB = (uint32_t)p.NB;
     const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
@@ -162,13 +170,13 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                   const uint32_t brow = (uint32_t)((kh * 3 + kw) * 3 + (d - (pl - 1))) * NB;   // kd' = d - pl + 1
                   const uint64_t bdesc = pack64(b_lo0 + brow * 2u, desc_hi);
                   const uint32_t idesc = idesc_base | (((uint32_t)m * NB >> 3) << 17);
-                  uint32_t a_lo = a_kh + 2u * (uint32_t)kw;
-                  uint32_t dcol = tmem_base + (uint32_t)s0 * NB;
-#pragma unroll 4
-                  for (int tt = 0; tt < T; ++tt) {
-                    if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, idesc, 1u);
-                    a_lo += tile16;
-                    dcol += tstep;
+                  uint32_t a_lo = a_kh + 2u * (uint32_t)kw + (uint32_t)ii * tile16;
+                  uint32_t dcol = tmem_base + (uint32_t)s0 * NB + (uint32_t)ii * tstep;
+#pragma unroll 2
+                  for (int tt = ii; tt < T; tt += S_ISSUERS) {
+                    if (!(p.dbg & 1) && elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, idesc, 1u);
+                    a_lo += S_ISSUERS * tile16;
+                    dcol += S_ISSUERS * tstep;
                   }
                   d += m;
                 }
@@ -226,7 +234,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               tmem_ld16(taddr + (uint32_t)c0, v);
               tmem_ld_wait();
               tmem_st16_zero(taddr + (uint32_t)c0);                     // hand the slot back zeroed
-              if (valid) {
+              if (valid && !(p.dbg & 4)) {
                 float f32[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -375,6 +383,7 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   SParams& p = pl.p;
   p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
   p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
+  { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (stat_sum) {
     ICH_REQUIRE(stat_sumsq != nullptr, "%s: fused statistics need both buffers", what);
     cudaMemsetAsync(stat_sum, 0, sizeof(double) * Cout, stream);
