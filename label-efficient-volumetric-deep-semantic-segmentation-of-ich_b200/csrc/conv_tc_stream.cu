@@ -150,35 +150,58 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             acquired = d;
           }
           tc_fence_after();
+          // The three live output planes lo..hi occupy <= 2 runs of consecutive ring slots (the ring wraps): resolve the runs ONCE per
+          // input plane -- accumulator column, instruction descriptor (N = run length * NB) and the depth-tap row offset inside a
+          // (kh, kw) weight group -- so that the per-tap work below is two adds and a pack per MMA.
+          uint32_t r_dcol0, r_idesc0, r_brow0, r_dcol1 = 0, r_idesc1 = 0, r_brow1 = 0;
+          bool two_runs;
+          {
+            const uint32_t g0 = (uint32_t)(g_base + (lo - d0));
+            const int s0 = (int)(g0 & 3u), cnt = hi - lo + 1;
+            const int m0 = min(cnt, SLOTS - s0);
+            r_dcol0 = tmem_base + (uint32_t)s0 * NB + (uint32_t)ii * tstep;
+            r_idesc0 = idesc_base | ((((uint32_t)m0 * NB) >> 3) << 17);
+            r_brow0 = (uint32_t)(lo - (pl - 1)) * NB * 2u;                 // kd' = d - pl + 1, rows of 32 B = 2 units
+            two_runs = m0 < cnt;
+            if (two_runs) {
+              r_dcol1 = tmem_base + (uint32_t)ii * tstep;                  // wrapped: slot 0
+              r_idesc1 = idesc_base | ((((uint32_t)(cnt - m0) * NB) >> 3) << 17);
+              r_brow1 = (uint32_t)(lo + m0 - (pl - 1)) * NB * 2u;
+            }
+          }
           for (int kc = 0; kc < p.KC; ++kc) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-            const uint32_t a_lo0 = ((sa & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t a_lo0 = (((sa & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)ii * tile16;
             const uint32_t b_addr = p.b_resident ? (w_base + (uint32_t)kc * p.b_bytes) : (sa + p.a_bytes);
-            const uint32_t b_lo0 = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
+            uint32_t b_tap = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
             uint32_t a_kh = a_lo0;
+            if (!(p.dbg & 1)) {
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
+              for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                int d = lo;
-                while (d <= hi) {                                       // <= 2 runs of consecutive ring slots
-                  const long long g = g_base + (d - d0);
-                  const int s0 = (int)(g & 3);
-                  const int m = min(hi - d + 1, SLOTS - s0);
-                  const uint32_t brow = (uint32_t)((kh * 3 + kw) * 3 + (d - (pl - 1))) * NB;   // kd' = d - pl + 1
-                  const uint64_t bdesc = pack64(b_lo0 + brow * 2u, desc_hi);
-                  const uint32_t idesc = idesc_base | (((uint32_t)m * NB >> 3) << 17);
-                  uint32_t a_lo = a_kh + 2u * (uint32_t)kw + (uint32_t)ii * tile16;
-                  uint32_t dcol = tmem_base + (uint32_t)s0 * NB + (uint32_t)ii * tstep;
+                for (int kw = 0; kw < 3; ++kw, b_tap += 6u * NB) {
+                  {
+                    const uint64_t bdesc = pack64(b_tap + r_brow0, desc_hi);
+                    uint32_t a_lo = a_kh + 2u * (uint32_t)kw, dcol = r_dcol0;
 #pragma unroll 2
-                  for (int tt = ii; tt < T; tt += S_ISSUERS) {
-                    if (!(p.dbg & 1) && elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, idesc, 1u);
-                    a_lo += S_ISSUERS * tile16;
-                    dcol += S_ISSUERS * tstep;
+                    for (int tt = ii; tt < T; tt += S_ISSUERS) {
+                      if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, r_idesc0, 1u);
+                      a_lo += S_ISSUERS * tile16;
+                      dcol += S_ISSUERS * tstep;
+                    }
                   }
-                  d += m;
+                  if (two_runs) {
+                    const uint64_t bdesc = pack64(b_tap + r_brow1, desc_hi);
+                    uint32_t a_lo = a_kh + 2u * (uint32_t)kw, dcol = r_dcol1;
+#pragma unroll 2
+                    for (int tt = ii; tt < T; tt += S_ISSUERS) {
+                      if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, r_idesc1, 1u);
+                      a_lo += S_ISSUERS * tile16;
+                      dcol += S_ISSUERS * tstep;
+                    }
+                  }
                 }
               }
             }
