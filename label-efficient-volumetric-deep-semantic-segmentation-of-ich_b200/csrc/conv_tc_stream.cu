@@ -36,7 +36,8 @@ struct SParams {
   int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA slab loads, 4 = no epilogue math / stores
 };
 
-constexpr int S_THREADS = 224;      // warp 0: TMA, warps 1 and 6: MMA issuers (even / odd tiles), warps 2..5: epilogue
+constexpr int S_THREADS = 384;      // warp 0: TMA, warps 1 and 2: MMA issuers (even / odd tiles), warp 3: idle, warps 4..11: epilogue (two per TMEM lane quadrant)
+constexpr int S_EPI_WARPS = 8;
 constexpr int S_ISSUERS = 2;
 constexpr int S_MAX_STAGES = 6;
 constexpr int SLOTS = 4;
@@ -47,8 +48,23 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+      "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t s_pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
-template <bool STATS>
+template <bool STATS, int SNB>
 __global__ void __launch_bounds__(S_THREADS, 1)
 conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const SParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -62,7 +78,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], S_ISSUERS); }
-    for (int a = 0; a < SLOTS; ++a) { mbar_init(&tfull_bar[a], S_ISSUERS); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < SLOTS; ++a) { mbar_init(&tfull_bar[a], S_ISSUERS); mbar_init(&tempty_bar[a], S_EPI_WARPS); }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
@@ -71,7 +87,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  if (warp >= 2 && warp <= 5) {   // all accumulator slots start out zero: every MMA accumulates
+  if (warp >= 4 && warp <= 7) {   // all accumulator slots start out zero: every MMA accumulates
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     for (uint32_t c = 0; c < (uint32_t)(p.T * SLOTS * p.NB); c += 16) tmem_st16_zero(lane_base + c);
     tmem_st_wait();
@@ -120,11 +136,11 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         }
       }
     }
-  } else if (warp == 1 || warp == 6) {
+  } else if (warp == 1 || warp == 2) {
     // ===================================================== MMA issuers.  The issue loop is bound by the latency of its own (uniform
     // datapath) instruction stream -- ~68 cycles per MMA measured with the MMAs themselves ablated, against 56 cycles of tensor
     // work for N = 96 -- so TWO warps on different SM sub-partitions issue the even and the odd tiles of every (plane, chunk, tap).
-    const int ii = warp == 1 ? 0 : 1;
+    const int ii = warp - 1;
     const uint32_t NB = (uint32_t)p.NB;
     const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
@@ -219,17 +235,44 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       }
       g_base += dend - d0;
     }
-  } else {
-    // ===================================================== epilogue warps (2..5)
-    const int q = warp & 3;
+  } else if (warp >= 4) {
+    // ===================================================== epilogue warps (4..11): TMEM lane quadrant = warp % 4, two warps per quadrant
+    // taking the even / odd tiles of every output plane.  One warp needs ~600 cycles per 16-column chunk (tcgen05.ld latency + a
+    // dependent instruction stream): with four warps the Cin <= 32 layers were bound by the epilogue, not by the MMAs.
+    const int q = warp & 3, eset = (warp - 4) >> 2;
     const int l = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float csum[STATS ? 64 : 1], csq[STATS ? 64 : 1];
+    float csum[STATS ? SNB : 1], csq[STATS ? SNB : 1];
     if (STATS) {
 #pragma unroll
-      for (int k = 0; k < 64; ++k) csum[k] = csq[k] = 0.f;
+      for (int k = 0; k < SNB; ++k) csum[k] = csq[k] = 0.f;
     }
     const int n0 = nb_fixed * p.NB;
+    const bool plain = !(p.dbg & 4);
+    // 16 accumulator columns -> bias / ReLU -> bf16 (-> statistics of the stored values) -> two 16-byte stores
+    auto emit16 = [&](const uint32_t* v, const int c0, bf16* yrow) __attribute__((always_inline)) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float a = __uint_as_float(v[2 * k]), b = __uint_as_float(v[2 * k + 1]);
+        if (!STATS) {
+          if (p.bias) { a += p.bias[n0 + c0 + 2 * k]; b += p.bias[n0 + c0 + 2 * k + 1]; }
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        }
+        pk[k] = s_pack_bf16x2(a, b);
+      }
+      if (STATS) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float lo = __uint_as_float(pk[k] << 16), hi = __uint_as_float(pk[k] & 0xffff0000u);
+          const int i0 = (c0 + 2 * k) % SNB, i1 = (c0 + 2 * k + 1) % SNB;
+          csum[i0] += lo; csq[i0] = fmaf(lo, lo, csq[i0]);
+          csum[i1] += hi; csq[i1] = fmaf(hi, hi, csq[i1]);
+        }
+      }
+      *reinterpret_cast<uint4*>(yrow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(yrow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
     long long g_base = 0;
     for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
       long long t = sp;
@@ -243,36 +286,34 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int slot = (int)(g & 3);
         mbar_wait(&tfull_bar[slot], (uint32_t)((g >> 2) & 1));
         tc_fence_after();
-        for (int tt = 0; tt < p.T; ++tt) {
+        for (int tt = eset; tt < p.T; tt += 2) {
           const int f = (p.row_mode ? tt * p.PW : tt * 128) + l;
           const int r = f / p.PW, pos = f - r * p.PW;
-          const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W);
+          const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W) && plain;
           const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
           bf16* yrow = p.y + vox * p.y_ld + n0;
           const uint32_t taddr = lane_base + (uint32_t)((tt * SLOTS + slot) * p.NB);
+          if ((p.NB & 31) == 0) {
 #pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 16) {
-            if (c0 < p.NB) {
-              uint32_t v[16];
-              tmem_ld16(taddr + (uint32_t)c0, v);
-              tmem_ld_wait();
-              tmem_st16_zero(taddr + (uint32_t)c0);                     // hand the slot back zeroed
-              if (valid && !(p.dbg & 4)) {
-                float f32[16];
+            for (int c0 = 0; c0 < 64; c0 += 32) {       // compile-time column offsets: the statistics stay in registers
+              if (c0 < p.NB) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                tmem_st16_zero(taddr + (uint32_t)c0);                   // hand the slot back zeroed
+                tmem_st16_zero(taddr + (uint32_t)c0 + 16u);
+                if (valid) { emit16(v, c0, yrow); emit16(v + 16, c0 + 16, yrow); }
+              }
+            }
+          } else {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                  float a = __uint_as_float(v[k]);
-                  if (p.bias) a += p.bias[n0 + c0 + k];
-                  if (p.relu) a = fmaxf(a, 0.f);
-                  f32[k] = a;
-                  if (STATS) {
-                    const float rv = __bfloat162float(__float2bfloat16_rn(a));
-                    csum[c0 + k] += rv;
-                    csq[c0 + k] = fmaf(rv, rv, csq[c0 + k]);
-                  }
-                }
-                Vec<bf16>::store(yrow + c0, f32);
-                Vec<bf16>::store(yrow + c0 + 8, f32 + 8);
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+              if (c0 < p.NB) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                tmem_st16_zero(taddr + (uint32_t)c0);
+                if (valid) emit16(v, c0, yrow);
               }
             }
           }
@@ -286,7 +327,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
     if (STATS) {
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
+      for (int k = 0; k < SNB; ++k) {
         if (k < p.NB) {
           const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
           if (lane == 0) {
@@ -434,8 +475,9 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_stream_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_stream_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_stream_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e != cudaSuccess) cudaGetLastError();
     ICH_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
     attr_set = true;
@@ -443,7 +485,8 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
   grid = grid / p.n_nb * p.n_nb;
   if (grid < p.n_nb) grid = p.n_nb;
-  if (stat_sum) conv_tc_stream_kernel<true><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else conv_tc_stream_kernel<false><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  if (stat_sum && p.NB <= 32) conv_tc_stream_kernel<true, 32><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else if (stat_sum) conv_tc_stream_kernel<true, 64><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else conv_tc_stream_kernel<false, 1><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
   return ich_check_launch(what);
 }
