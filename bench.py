@@ -55,32 +55,59 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Sampled through NVML in-process (the
+    library nvidia-smi itself queries): forking `nvidia-smi` every 100 ms from a Python thread stalled the launch loop of the
+    end-to-end pass (GIL + driver locks); `nvidia-smi` stays as the fallback when pynvml is unavailable."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    # nvmlClocksEventReason* bit masks
+    BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        get = getattr(n, 'nvmlDeviceGetCurrentClocksEventReasons', None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mask = int(get(self.handle))
+        return [str(sm), str(self.max_sm)] + ['Active' if mask & bit else 'Not Active' for _, bit in self.BITS]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(',')])
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([f.strip() for f in out.split(',')])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02 if self.nvml is not None else 0.5)
 
     def summary(self):
         sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        names = [n for n, _ in self.BITS]
         reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith('active') for s in self.samples)]
         mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace('.', '').isdigit()]
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(self.samples)}
+                'samples': len(self.samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def cpu_reference_step(sample_shape, threads, max_seconds=25.0, steps=3, warmup=1):
@@ -251,11 +278,13 @@ def main():
     # one batch of look-ahead on a side stream = ich_b200.staging.DevicePrefetcher) and the loss is read back to the host
     from ich_b200.staging import DevicePrefetcher
 
-    def e2e_run(steps):
-        for x, m in DevicePrefetcher([(xh, mh)] * steps, dev):
+    prefetch = DevicePrefetcher([(xh, mh)] * args.steps, dev)      # one prefetcher for the run, like one per DataLoader in a trainer
+
+    def e2e_run():
+        for x, m in prefetch:
             step(x, m).item()
-    e2e_run(2)
-    t_e2e = timed(lambda: e2e_run(args.steps), 1)
+    e2e_run()
+    t_e2e = timed(e2e_run, 1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

@@ -53,17 +53,25 @@ class DevicePrefetcher:
         # the buffer set being overwritten was handed out SETS batches ago; order the copy after the compute stream's work
         # enqueued so far (which includes every kernel that read it), then overlap with the step launched next
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        # Device buffers are created under the COMPUTE stream (the caching allocator keeps one pool per stream: a buffer first
+        # requested under a fresh side stream is a synchronous cudaMalloc -- measured +2..8 ms per step until all sets exist).
         slot = [0]
+        pairs = []
+
+        def reserve(t):
+            if t.is_cuda:
+                return t
+            i = slot[0]
+            slot[0] += 1
+            if not t.is_pinned():
+                t = t.pin_memory()
+            buf = self._buffer(i, t)
+            pairs.append((buf, t))
+            return buf
+        out = _map(batch, reserve)
         with torch.cuda.stream(self.stream):
-            def put(t):
-                if t.is_cuda:
-                    return t
-                i = slot[0]
-                slot[0] += 1
-                if not t.is_pinned():
-                    t = t.pin_memory()
-                return self._buffer(i, t).copy_(t, non_blocking=True)
-            out = _map(batch, put)
+            for buf, t in pairs:
+                buf.copy_(t, non_blocking=True)
         self._turn += 1
         return out
 
