@@ -515,10 +515,13 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     {
       int stage = 0; uint32_t phase = 0;
       for (long long item = it_begin; item < it_end; ++item) {
+        // depth is the FASTEST item index: consecutive items of a CTA are the same (row block, w block) at d, d + 1, ... so two of the
+        // three x planes of an item were loaded by the previous one and are still in L2 (with depth slowest the re-reads went to DRAM:
+        // the full-resolution layers were DRAM-bound at 3x the algorithmic bytes)
         long long t = item;
+        const int d = (int)(t % p.D); t /= p.D;
         const int wb = (int)(t % p.n_wb); t /= p.n_wb;
-        const int rb = (int)(t % p.n_rb); t /= p.n_rb;
-        const int d = (int)(t % p.D); const int n = (int)(t / p.D);
+        const int rb = (int)(t % p.n_rb); const int n = (int)(t / p.n_rb);
         const int w0 = wb * p.WB, h0 = rb * p.R;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes + p.a_off;

@@ -83,7 +83,12 @@ def test_conv_bn_relu_unit(prec, training, chan):
     conv_c, bn_c = copy.deepcopy(conv).to(DEV), copy.deepcopy(bn).to(DEV)
     conv.train(training); bn.train(training)
     xr = x.clone().requires_grad_(True)
-    zr = F.relu(bn(conv(xr)))
+    ar = bn(conv(xr))
+    zr = F.relu(ar)
+    # knife-edge elements: a pre-activation within rounding distance of 0 may get the opposite ReLU mask on the two sides (different
+    # summation orders; the CPU conv is not even run-to-run deterministic) and ONE flipped element of 5e5 is a 1e-3 relative error
+    # of the data gradient.  Give those elements no upstream gradient, so the comparison tests the arithmetic, not the coin flip.
+    dz = dz * (ar.detach().abs() > 2e-3)
     zr.backward(dz)
     with config.override(precision=prec):
         dt = config.act_dtype()
