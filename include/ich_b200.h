@@ -101,6 +101,15 @@ int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const flo
                    const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype, long long M, int C, int relu,
                    int training, void* stream);
 
+/* same two operators with nn.Dropout (models/networks/UNet.py:150,175-176: after the second ReLU of a ConvBlock) fused in:
+ * z = relu(y*scale+shift) * keep/(1-p), keep = Philox4x32-10(seed; row, channel) >= p (16-bit resolution); the backward
+ * regenerates the mask from the same (seed, row, channel) -- no mask tensor.  drop_p == 0 is the plain operator.          */
+int ich_affine_act_drop(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C,
+                        int relu, float drop_p, long long seed, void* stream);
+int ich_bn_act_bwd_drop(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype, long long M, int C,
+                        int relu, int training, float drop_p, long long seed, void* stream);
+
 /* ---- nn.MaxPool3d/2d(2,2) (models/networks/UNet.py:82,109); grid args = the INPUT grid ------------------------------ */
 int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
 /* dskip (optional): gradient of the SAME tensor arriving through the skip connection (UNet.py:107,119), added in the same pass */

@@ -60,11 +60,12 @@ class ConvBlock(nn.Module):
         self.conv2 = conv(in_channels=mid_channels, out_channels=out_channels, kernel_size=kernel_size, padding=1)
         self.bn2 = bn(out_channels)
 
-    def _unit(self, x, conv, bn, concat_c=0):
+    def _unit(self, x, conv, bn, concat_c=0, drop_p=0.0):
         if conv.padding[0] * 2 + 1 != conv.kernel_size[0]:
             _not_built(f'kernel_size={conv.kernel_size} with padding={conv.padding}')
         training = self.training or not bn.track_running_stats
-        z = ops.ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, True, concat_c)
+        z = ops.ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, True, concat_c,
+                                 drop_p)
         if concat_c:
             z, buf = z
             z._ich_concat_buf = buf          # the decoder's UpConvCat completes this buffer in place (zero-copy skip concat)
@@ -74,13 +75,12 @@ class ConvBlock(nn.Module):
 
     def forward_cl(self, x, concat_c=0):
         """Channel-last engine path: x [N, D, H, W, C] in the engine dtype. concat_c > 0: the block output is laid out as the
-        first channel slab of a [.., C + concat_c] buffer (it will be the skip half of a decoder concat)."""
-        use_dropout = self.dropout.p > 0.0 and self.training
+        first channel slab of a [.., C + concat_c] buffer (it will be the skip half of a decoder concat).
+        nn.Dropout (reference UNet.py:175-176) is fused into the second unit's BN-apply / BN-backward kernels (counter-based
+        Philox mask, no mask tensor); being RNG-dependent it matches the reference statistically, not element-wise."""
+        drop_p = float(self.dropout.p) if (self.dropout.p > 0.0 and self.training) else 0.0
         x = self._unit(x, self.conv1, self.bn1)
-        x = self._unit(x, self.conv2, self.bn2, 0 if use_dropout else concat_c)
-        if use_dropout:
-            x = self.dropout(x)      # elementwise, RNG-dependent (SURVEY section 7): torch's Philox dropout on the engine tensor
-        return x
+        return self._unit(x, self.conv2, self.bn2, concat_c, drop_p)
 
     def forward(self, input):
         was_4d = input.dim() == 4

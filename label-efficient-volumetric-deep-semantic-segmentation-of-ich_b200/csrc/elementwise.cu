@@ -12,6 +12,52 @@ __host__ __device__ inline bool vec_ok(const void* p, int ld, int C) {
   return (C % Vec<T>::N == 0) && (ld % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
 
+// ---- fused dropout (nn.Dropout after the second ReLU of a ConvBlock, reference models/networks/UNet.py:150,175-176) -------------
+// Counter-based: the keep decision of element (row r, channel c) is a pure function of (seed, r, c), so the forward kernel and the
+// two backward kernels regenerate the same mask and no mask tensor is ever stored.  One Philox4x32-10 block yields eight 16-bit
+// uniforms = the eight channels c & ~7 .. (c & ~7) + 7 of a row; keep iff u16 >= thr, thr = round(p * 65536), kept values are
+// scaled by 65536 / (65536 - thr).  thr == 0 disables the whole thing (uniform branch).
+struct Drop {
+  uint32_t thr;
+  float scale;
+  uint32_t seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ k0, lo1, hi0 ^ ctr.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+// keep multipliers (0 or scale) of the V channels c .. c + V - 1 of row r  (V in {1, 4, 8}, c % V == 0)
+template <int V>
+__device__ __forceinline__ void drop_mult(const Drop& d, long long r, int c, float* m) {
+  const uint4 u = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)((unsigned long long)r >> 32), (uint32_t)(c >> 3), 0x1C4B200u), d.seed_lo, d.seed_hi);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int h = (c & 7) + k;                       // half-word index 0..7
+    const uint32_t v16 = (w[h >> 1] >> ((h & 1) * 16)) & 0xffffu;
+    m[k] = v16 >= d.thr ? d.scale : 0.f;
+  }
+}
+
+inline Drop make_drop(float p, unsigned long long seed) {
+  Drop d{0u, 1.f, (uint32_t)seed, (uint32_t)(seed >> 32)};
+  if (p > 0.f) {
+    double t = (double)p * 65536.0 + 0.5;
+    d.thr = t >= 65536.0 ? 65536u : (uint32_t)t;
+    if (d.thr == 0) d.thr = 1;                       // p > 0 below the 16-bit resolution: smallest representable rate
+    d.scale = d.thr >= 65536u ? 0.f : (float)(65536.0 / (65536.0 - (double)d.thr));
+  }
+  return d;
+}
+
 inline int grid_for(long long work, int threads, int per_sm = 8) {
   long long blocks = (work + threads - 1) / threads;
   long long cap = (long long)ich_num_sms() * per_sm;
@@ -190,7 +236,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, T* __restrict__ z, int z_ld, long long M, int C,
-                                                         int relu) {
+                                                         int relu, const Drop drop) {
   constexpr int V = VEC ? Vec<T>::N : 1;
   const int groups = C / V;
   const long long total = M * groups;
@@ -204,6 +250,12 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ y
       float t = fmaf(v[k], scale[c + k], shift[c + k]);
       v[k] = relu ? fmaxf(t, 0.f) : t;
     }
+    if (drop.thr) {
+      float m[V];
+      drop_mult<V>(drop, r, c, m);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] *= m[k];
+    }
     if (VEC) Vec<T>::store(z + r * z_ld + c, v); else z[r * z_ld + c] = from_f32<T>(v[0]);
   }
 }
@@ -214,7 +266,7 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
                                                             const float* __restrict__ scale, const float* __restrict__ shift,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd, long long M,
-                                                            int C, int relu, double* __restrict__ sums /*[2][C]*/, int rows_per_block) {
+                                                            int C, int relu, double* __restrict__ sums /*[2][C]*/, int rows_per_block, const Drop drop) {
   constexpr int V = VEC ? Vec<T>::N : 1;
   const int groups = C / V;
   const int lanes = max(1, 256 / groups);
@@ -234,6 +286,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
       float a[V], b[V];
       if (VEC) { Vec<T>::load(dz + r * dz_ld + c, a); Vec<T>::load(y + r * y_ld + c, b); }
       else { a[0] = to_f32(dz[r * dz_ld + c]); b[0] = to_f32(y[r * y_ld + c]); }
+      if (drop.thr) {
+        float m[V];
+        drop_mult<V>(drop, r, c, m);
+#pragma unroll
+        for (int k = 0; k < V; ++k) a[k] *= m[k];
+      }
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         float gk = (!relu || fmaf(b[k], sc[k], sf[k]) > 0.f) ? a[k] : 0.f;
@@ -257,7 +315,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const double* __restrict__ sums, T* __restrict__ dy, int dy_ld, long long M, int C,
-                                                           int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                           int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta, const Drop drop) {
   constexpr int V = VEC ? Vec<T>::N : 1;
   const int groups = C / V;
   const long long total = M * groups;
@@ -273,6 +331,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     float a[V], b[V], o[V];
     if (VEC) { Vec<T>::load(dz + r * dz_ld + c, a); Vec<T>::load(y + r * y_ld + c, b); }
     else { a[0] = to_f32(dz[r * dz_ld + c]); b[0] = to_f32(y[r * y_ld + c]); }
+    if (drop.thr) {
+      float m[V];
+      drop_mult<V>(drop, r, c, m);
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] *= m[k];
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float sc = scale[c + k];
@@ -289,7 +353,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 //      in registers, no index division in the loop) and strides over rows with several independent loads in flight. ---------
 template <typename T>
 __global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
-                                                              const float* __restrict__ shift, T* __restrict__ z, int z_ld, long long M, int C, int relu) {
+                                                              const float* __restrict__ shift, T* __restrict__ z, int z_ld, long long M, int C, int relu,
+                                                              const Drop drop) {
   constexpr int V = Vec<T>::N;
   const int groups = C / V, rpb = 256 / groups;
   const int c = (threadIdx.x % groups) * V;
@@ -307,6 +372,12 @@ __global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restric
       a[k] = fmaf(a[k], sc[k], sh[k]); b[k] = fmaf(b[k], sc[k], sh[k]);
       if (relu) { a[k] = fmaxf(a[k], 0.f); b[k] = fmaxf(b[k], 0.f); }
     }
+    if (drop.thr) {
+      float m0[V], m1[V];
+      drop_mult<V>(drop, r, c, m0); drop_mult<V>(drop, r + step, c, m1);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { a[k] *= m0[k]; b[k] *= m1[k]; }
+    }
     Vec<T>::store(z + r * z_ld + c, a);
     Vec<T>::store(z + (r + step) * z_ld + c, b);
   }
@@ -315,6 +386,12 @@ __global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restric
     Vec<T>::load(y + r * y_ld + c, a);
 #pragma unroll
     for (int k = 0; k < V; ++k) { a[k] = fmaf(a[k], sc[k], sh[k]); if (relu) a[k] = fmaxf(a[k], 0.f); }
+    if (drop.thr) {
+      float m0[V];
+      drop_mult<V>(drop, r, c, m0);
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] *= m0[k];
+    }
     Vec<T>::store(z + r * z_ld + c, a);
   }
 }
@@ -323,7 +400,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd, long long M, int C,
-                                                                 int relu, double* __restrict__ sums) {
+                                                                 int relu, double* __restrict__ sums, const Drop drop) {
   constexpr int V = Vec<T>::N;
   constexpr int U = 4;                       // rows in flight per thread: 8 independent 16-byte loads
   const int groups = C / V, rpb = 256 / groups;
@@ -337,6 +414,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
     float a[U][V], b[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) { Vec<T>::load(dz + (r + u * step) * dz_ld + c, a[u]); Vec<T>::load(y + (r + u * step) * y_ld + c, b[u]); }
+    if (drop.thr) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float m[V];
+        drop_mult<V>(drop, r + u * step, c, m);
+#pragma unroll
+        for (int k = 0; k < V; ++k) a[u][k] *= m[k];
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -349,6 +435,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
   for (; r < M; r += step) {
     float a0[V], b0[V];
     Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
+    if (drop.thr) {
+      float m[V];
+      drop_mult<V>(drop, r, c, m);
+#pragma unroll
+      for (int k = 0; k < V; ++k) a0[k] *= m[k];
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
@@ -370,7 +462,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const double* __restrict__ sums, T* __restrict__ dy, int dy_ld, long long M, int C,
-                                                                int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                const Drop drop) {
   constexpr int V = Vec<T>::N;
   const int groups = C / V, rpb = 256 / groups;
   const int c = (threadIdx.x % groups) * V;
@@ -394,6 +487,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
     float a0[V], b0[V], a1[V], b1[V];
     Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
     Vec<T>::load(dz + (r + step) * dz_ld + c, a1); Vec<T>::load(y + (r + step) * y_ld + c, b1);
+    if (drop.thr) {
+      float m0[V], m1[V];
+      drop_mult<V>(drop, r, c, m0); drop_mult<V>(drop, r + step, c, m1);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { a0[k] *= m0[k]; a1[k] *= m1[k]; }
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
@@ -407,6 +506,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
   if (r < M) {
     float a0[V], b0[V];
     Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
+    if (drop.thr) {
+      float m0[V];
+      drop_mult<V>(drop, r, c, m0);
+#pragma unroll
+      for (int k = 0; k < V; ++k) a0[k] *= m0[k];
+    }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? a0[k] : 0.f;
@@ -636,45 +741,70 @@ int ich_bn_finalize(const double* sum, const double* sumsq, long long count, int
   return ich_check_launch("ich_bn_finalize");
 }
 
-int ich_affine_act(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C,
-                   int relu, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
+static int affine_act_impl(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C,
+                           int relu, const Drop drop, cudaStream_t s, const char* what) {
   if (M * C == 0) return 0;
-  DISPATCH_T(dtype, "ich_affine_act", {
+  DISPATCH_T(dtype, what, {
     if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C) && rows_fast_ok(C, Vec<T>::N))
-      affine_act_rows_kernel<T><<<rows_grid(M, C, Vec<T>::N), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
+      affine_act_rows_kernel<T><<<rows_grid(M, C, Vec<T>::N), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
     else if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C))
-      affine_act_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
+      affine_act_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
     else
-      affine_act_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu);
+      affine_act_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
   })
-  return ich_check_launch("ich_affine_act");
+  return ich_check_launch(what);
 }
 
-int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
-                   const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
-                   long long M, int C, int relu, int training, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
+int ich_affine_act(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C,
+                   int relu, void* stream) {
+  return affine_act_impl(y, y_ld, scale, shift, z, z_ld, dtype, M, C, relu, make_drop(0.f, 0), (cudaStream_t)stream, "ich_affine_act");
+}
+
+int ich_affine_act_drop(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C,
+                        int relu, float drop_p, long long seed, void* stream) {
+  ICH_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, "ich_affine_act_drop: dropout probability %g outside [0, 1]", (double)drop_p);
+  return affine_act_impl(y, y_ld, scale, shift, z, z_ld, dtype, M, C, relu, make_drop(drop_p, (unsigned long long)seed), (cudaStream_t)stream,
+                         "ich_affine_act_drop");
+}
+
+static int bn_act_bwd_impl(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                           const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                           long long M, int C, int relu, int training, const Drop drop, cudaStream_t s, const char* what) {
   if (M * C == 0) return 0;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
   const int rows_per_block = 2048;
   unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
   size_t shbytes = sizeof(float) * 2 * C;
-  DISPATCH_T(dtype, "ich_bn_act_bwd", {
+  DISPATCH_T(dtype, what, {
     bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
     if (vec && rows_fast_ok(C, Vec<T>::N)) {
       const int grid = rows_grid(M, C, Vec<T>::N);
-      bn_bwd_reduce_rows_kernel<T><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums);
-      bn_bwd_apply_rows_kernel<T><<<grid, 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta);
+      bn_bwd_reduce_rows_kernel<T><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
+      bn_bwd_apply_rows_kernel<T><<<grid, 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
     } else if (vec) {
-      bn_bwd_reduce_kernel<T, true><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block);
-      bn_bwd_apply_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta);
+      bn_bwd_reduce_kernel<T, true><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
+      bn_bwd_apply_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
     } else {
-      bn_bwd_reduce_kernel<T, false><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block);
-      bn_bwd_apply_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta);
+      bn_bwd_reduce_kernel<T, false><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
+      bn_bwd_apply_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
     }
   })
-  return ich_check_launch("ich_bn_act_bwd");
+  return ich_check_launch(what);
+}
+
+int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                   const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                   long long M, int C, int relu, int training, void* stream) {
+  return bn_act_bwd_impl(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, dtype, M, C, relu, training,
+                         make_drop(0.f, 0), (cudaStream_t)stream, "ich_bn_act_bwd");
+}
+
+int ich_bn_act_bwd_drop(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                        long long M, int C, int relu, int training, float drop_p, long long seed, void* stream) {
+  ICH_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, "ich_bn_act_bwd_drop: dropout probability %g outside [0, 1]", (double)drop_p);
+  return bn_act_bwd_impl(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, dtype, M, C, relu, training,
+                         make_drop(drop_p, (unsigned long long)seed), (cudaStream_t)stream, "ich_bn_act_bwd_drop");
 }
 
 int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {

@@ -294,7 +294,10 @@ def from_channels_last(x, was_4d=False):
 # ---------------------------------------------------------------------------------------------------------------
 class ConvBnRelu(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, relu, concat_c=0):
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, relu, concat_c=0, drop_p=0.0):
+        """drop_p > 0: nn.Dropout(p) applied to the unit's output (reference UNet.py:175-176) fused into the BN-apply kernel; the
+        mask is a function of (seed, voxel, channel) and is regenerated in backward.  The seed is drawn from torch's default CPU
+        generator, so torch.manual_seed makes runs reproducible (UNet2D_scripts.py:53-60)."""
         n, d, h, w, cin = x.shape
         cout = weight.shape[0]
         m = n * d * h * w
@@ -336,10 +339,16 @@ class ConvBnRelu(Function):
             buf = None
             z = torch.empty_like(y)
             zld = cout
-        call('ich_affine_act', y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), z.data_ptr(), zld, _dt(y), m, cout, int(relu),
-             _stream())
+        drop_p = float(drop_p)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0.0 else 0
+        if drop_p > 0.0:
+            call('ich_affine_act_drop', y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), z.data_ptr(), zld, _dt(y), m, cout,
+                 int(relu), drop_p, seed, _stream())
+        else:
+            call('ich_affine_act', y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), z.data_ptr(), zld, _dt(y), m, cout, int(relu),
+                 _stream())
         ctx.save_for_backward(x, weight, y, stats)
-        ctx.training, ctx.relu = training, relu
+        ctx.training, ctx.relu, ctx.drop = training, relu, (drop_p, seed)
         if concat_c:
             ctx.mark_non_differentiable(buf)
             return z, buf
@@ -359,9 +368,14 @@ class ConvBnRelu(Function):
         sums = torch.empty((2, cout), dtype=torch.float64, device=y.device)
         dgamma = torch.empty(cout, dtype=torch.float32, device=y.device)
         dbeta = torch.empty(cout, dtype=torch.float32, device=y.device)
-        call('ich_bn_act_bwd', dzp, dzld, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
-             stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(), _dt(y), m, cout, int(ctx.relu),
-             int(ctx.training), _stream())
+        if ctx.drop[0] > 0.0:
+            call('ich_bn_act_bwd_drop', dzp, dzld, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                 stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(), _dt(y), m, cout, int(ctx.relu),
+                 int(ctx.training), ctx.drop[0], ctx.drop[1], _stream())
+        else:
+            call('ich_bn_act_bwd', dzp, dzld, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                 stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(), _dt(y), m, cout, int(ctx.relu),
+                 int(ctx.training), _stream())
         need = ctx.needs_input_grad
         dx = conv_dgrad(dy, weight) if need[0] else None
         dw = conv_wgrad(x, dy, weight) if need[1] else None
@@ -369,7 +383,7 @@ class ConvBnRelu(Function):
         if need[2]:
             # training: d(loss)/d(bias) is exactly 0 (BatchNorm removes the mean); eval: sum of dy
             db = torch.zeros(cout, dtype=torch.float32, device=y.device) if ctx.training else col_sum(dy).float()
-        return dx, dw, db, (dgamma if need[3] else None), (dbeta if need[4] else None), None, None, None, None, None
+        return dx, dw, db, (dgamma if need[3] else None), (dbeta if need[4] else None), None, None, None, None, None, None
 
 
 class ConvBias(Function):

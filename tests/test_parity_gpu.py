@@ -111,6 +111,90 @@ def test_conv_bn_relu_unit(prec, training, chan):
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('p', [0.5, 0.1])
+def test_fused_dropout_unit(prec, p):
+    """nn.Dropout(p) after the unit (reference UNet.py:175-176), fused into the BN-apply / BN-backward kernels.  The mask is
+    RNG-dependent, so: (i) the drop rate is p within sampling error, (ii) kept values equal the undropped output / (1 - p),
+    (iii) with the mask read back from the output, every gradient equals the torch reference that applies the SAME mask,
+    (iv) the same seed reproduces the mask, a new seed changes it, and eval mode is the identity."""
+    g = torch.Generator().manual_seed(11)
+    cin, cout, n, d, h, w = 16, 32, 2, 8, 16, 16
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    conv = torch.nn.Conv3d(cin, cout, 3, padding=1)
+    bn = torch.nn.BatchNorm3d(cout)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0.3, 0.3, generator=g)
+    dz = torch.randn(n, cout, d, h, w, generator=g)
+    if prec == 'bf16':
+        x, dz = x.bfloat16().float(), dz.bfloat16().float()
+        with torch.no_grad():
+            conv.weight.copy_(conv.weight.bfloat16().float())
+    import copy
+    conv_c, bn_c = copy.deepcopy(conv).to(DEV), copy.deepcopy(bn).to(DEV)
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+
+        def run(seed, drop):
+            torch.manual_seed(seed)
+            bn_t = copy.deepcopy(bn_c)
+            xc = cl(x, dt).requires_grad_(True)
+            z = ops.ConvBnRelu.apply(xc, conv_c.weight, conv_c.bias, bn_t.weight, bn_t.bias, bn_t.running_mean, bn_t.running_var, True, True, 0, drop)
+            return xc, z
+        _, z0 = run(1, 0.0)
+        xc, z1 = run(1, p)
+        _, z1b = run(1, p)
+        _, z2 = run(2, p)
+        conv_c.weight.grad = None
+        z1.backward(cl(dz, dt))
+    z0n, z1n = nc(z0), nc(z1)
+    live = z0n > 0
+    keep = (z1n != 0) & live
+    rate = 1.0 - keep.sum().item() / live.sum().item()
+    assert abs(rate - p) < 0.01, rate                                          # ~1e5 live elements: 3 sigma ~ 0.005
+    scale = 65536.0 / (65536.0 - round(p * 65536))
+    assert rel(z1n[keep], z0n[keep] * scale) < (1e-6 if prec == 'fp32' else 6e-3)   # bf16: one more rounding of the scaled value
+    assert (z1n[~live] == 0).all()
+    assert torch.equal(z1.cpu(), z1b.cpu()) and not torch.equal(z1.cpu(), z2.cpu())
+    # torch reference with the same mask (knife-edge ReLU elements get no upstream gradient, see test_conv_bn_relu_unit)
+    xr = x.clone().requires_grad_(True)
+    ar = bn(conv(xr))
+    dzm = dz * (ar.detach().abs() > 2e-3)
+    zr = F.relu(ar) * keep.float() * scale
+    zr.backward(dzm)
+    with config.override(precision=prec):
+        conv_c.weight.grad = None
+        torch.manual_seed(1)
+        bn_t = copy.deepcopy(bn_c)
+        xc = cl(x, dt).requires_grad_(True)
+        z = ops.ConvBnRelu.apply(xc, conv_c.weight, conv_c.bias, bn_t.weight, bn_t.bias, bn_t.running_mean, bn_t.running_var, True, True, 0, p)
+        z.backward(cl(dzm, dt))
+    gt = TOL[prec] if prec == 'fp32' else 6e-2
+    assert rel(nc(z), zr) < TOL[prec]
+    assert rel(nc(xc.grad), xr.grad) < gt
+    assert rel(conv_c.weight.grad, conv.weight.grad) < gt
+    assert rel(bn_t.weight.grad, bn.weight.grad) < gt and rel(bn_t.bias.grad, bn.bias.grad) < gt
+
+
+def test_dropout_in_drop_in_block():
+    """ConvBlock(p_dropout=0.5): training drops ~half of the live outputs, eval is deterministic and undropped."""
+    from src.models.networks.UNet import ConvBlock
+    torch.manual_seed(0)
+    blk = ConvBlock(4, 16, mid_channels=8, use_3D=True, p_dropout=0.5).to(DEV)
+    x = torch.randn(2, 4, 8, 16, 16, device=DEV)
+    with config.override(precision='fp32'):
+        blk.train()
+        y1 = blk(x)
+        y1.sum().backward()
+        assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in blk.parameters())
+        blk.eval()
+        e1, e2 = blk(x), blk(x)
+    assert torch.equal(e1, e2)
+    frac = (y1 == 0).float().mean().item()
+    assert 0.6 < frac < 0.9            # ~half are zero from the ReLU, half of the rest from the dropout
+    assert (e1 == 0).float().mean().item() < frac - 0.15
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
 @pytest.mark.parametrize('fd', [2, 1])
 def test_maxpool_with_ties(prec, fd):
     g = torch.Generator().manual_seed(4)
