@@ -116,6 +116,11 @@ int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int 
 int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W, int C,
                      int FD, const void* dskip, int dskip_ld, void* stream);
 
+/* ---- nn.Upsample(scale_factor=2, trilinear / bilinear, align_corners=True): the bilinear=True decoder (models/networks/UNet.py:69-72,117).
+ *      Grid args = the INPUT grid; FD = depth factor (2 for 3-D, 1 for 2-D); y / dy may be a channel slab of the concat buffer.    */
+int ich_upsample2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
+int ich_upsample2_bwd(const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
+
 /* ---- torch.cat([res, x], 1) (models/networks/UNet.py:119) as channel-slab copies; AdaptiveAvgPool(1) (:295,318) ------ */
 int ich_slab_copy(const void* src, int src_ld, void* dst, int dst_ld, int dtype, long long M, int C, void* stream);
 int ich_avgpool_fwd(const void* x, int ld, int dtype, float* out, int N, long long S, int C, void* stream);

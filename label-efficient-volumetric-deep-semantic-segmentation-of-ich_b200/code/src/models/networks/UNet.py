@@ -182,8 +182,9 @@ class _UNetBase(nn.Module):
 
     def _decode(self, x, res):
         for up, block, r in zip(self.up_samp, self.up_block, res[::-1]):     # UNet.py:117-119
-            if not isinstance(up, (nn.ConvTranspose3d, nn.ConvTranspose2d)):
-                _not_built('bilinear=True (nn.Upsample decoder)')
+            if isinstance(up, nn.Upsample):                                     # bilinear=True: UNet.py:69-72
+                x = block.forward_cl(ops.UpsampleCat.apply(x, r, self._fd))
+                continue
             x = block.forward_cl(ops.UpConvCat.apply(x, r, up.weight, up.bias, self._fd, getattr(r, '_ich_concat_buf', None)))
         return x
 

@@ -640,6 +640,111 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const T* __restrict
 }
 
 
+// ---- nn.Upsample(scale_factor=2, mode='trilinear'/'bilinear', align_corners=True) of the bilinear=True decoder
+//      (reference models/networks/UNet.py:69-72,117).  ATen's index arithmetic in fp32: ratio = (I-1)/(O-1), src = ratio*o,
+//      i0 = (int)src, i1 = i0 + (i0 < I-1), w1 = src - i0.  Grid args = the INPUT grid; the output (FD*D, 2H, 2W) may be a channel
+//      slab of the concat buffer.  Backward is the gather form (deterministic): every input voxel sums the output voxels whose
+//      two taps per dimension include it.
+struct UpAxis { int I, O; float ratio; };
+__device__ __forceinline__ void up_src(const UpAxis& a, int o, int& i0, int& i1, float& w1) {
+  const float src = a.ratio * (float)o;
+  i0 = (int)src;
+  if (i0 > a.I - 1) i0 = a.I - 1;
+  i1 = i0 + (i0 < a.I - 1 ? 1 : 0);
+  w1 = src - (float)i0;
+}
+// weight with which output index o reads input index i along one axis
+__device__ __forceinline__ float up_w(const UpAxis& a, int o, int i) {
+  int i0, i1; float w1;
+  up_src(a, o, i0, i1, w1);
+  return (i0 == i ? 1.f - w1 : 0.f) + (i1 == i ? w1 : 0.f);
+}
+// candidate output range [lo, hi] for input index i: src(o) in (i - 1, i + 1)
+__device__ __forceinline__ void up_range(const UpAxis& a, int i, int& lo, int& hi) {
+  if (a.ratio <= 0.f) { lo = 0; hi = a.O - 1; return; }
+  lo = (int)floorf((float)(i - 1) / a.ratio); hi = (int)ceilf((float)(i + 1) / a.ratio);
+  if (lo < 0) lo = 0;
+  if (hi > a.O - 1) hi = a.O - 1;
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) upsample2_fwd_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int N, UpAxis ad,
+                                                            UpAxis ah, UpAxis aw, int C) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V;
+  const long long total = (long long)N * ad.O * ah.O * aw.O * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int c = (int)(t % groups) * V; t /= groups;
+    const int ow = (int)(t % aw.O); t /= aw.O;
+    const int oh = (int)(t % ah.O); t /= ah.O;
+    const int od = (int)(t % ad.O); const long long n = t / ad.O;
+    int d0, d1, h0, h1, w0, w1; float fd, fh, fw;
+    up_src(ad, od, d0, d1, fd); up_src(ah, oh, h0, h1, fh); up_src(aw, ow, w0, w1, fw);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+      const int dd = (corner & 4) ? d1 : d0, hh = (corner & 2) ? h1 : h0, ww = (corner & 1) ? w1 : w0;
+      const float wt = ((corner & 4) ? fd : 1.f - fd) * ((corner & 2) ? fh : 1.f - fh) * ((corner & 1) ? fw : 1.f - fw);
+      const long long src = (((n * ad.I + dd) * ah.I + hh) * aw.I + ww) * (long long)x_ld + c;
+      float v[V];
+      if (VEC) Vec<T>::load(x + src, v); else v[0] = to_f32(x[src]);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+    }
+    const long long dst = (((n * ad.O + od) * ah.O + oh) * aw.O + ow) * (long long)y_ld + c;
+    if (VEC) Vec<T>::store(y + dst, acc); else y[dst] = from_f32<T>(acc[0]);
+  }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const T* __restrict__ dy, int dy_ld, T* __restrict__ dx, int dx_ld, int N, UpAxis ad,
+                                                            UpAxis ah, UpAxis aw, int C) {
+  constexpr int V = VEC ? Vec<T>::N : 1;
+  const int groups = C / V;
+  const long long total = (long long)N * ad.I * ah.I * aw.I * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int c = (int)(t % groups) * V; t /= groups;
+    const int iw = (int)(t % aw.I); t /= aw.I;
+    const int ih = (int)(t % ah.I); t /= ah.I;
+    const int id = (int)(t % ad.I); const long long n = t / ad.I;
+    int dlo, dhi, hlo, hhi, wlo, whi;
+    up_range(ad, id, dlo, dhi); up_range(ah, ih, hlo, hhi); up_range(aw, iw, wlo, whi);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int od = dlo; od <= dhi; ++od) {
+      const float wd = up_w(ad, od, id);
+      if (wd == 0.f) continue;
+      for (int oh = hlo; oh <= hhi; ++oh) {
+        const float wh = wd * up_w(ah, oh, ih);
+        if (wh == 0.f) continue;
+        for (int ow = wlo; ow <= whi; ++ow) {
+          const float wt = wh * up_w(aw, ow, iw);
+          if (wt == 0.f) continue;
+          const long long src = (((n * ad.O + od) * ah.O + oh) * aw.O + ow) * (long long)dy_ld + c;
+          float v[V];
+          if (VEC) Vec<T>::load(dy + src, v); else v[0] = to_f32(dy[src]);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+        }
+      }
+    }
+    const long long dst = (((n * ad.I + id) * ah.I + ih) * aw.I + iw) * (long long)dx_ld + c;
+    if (VEC) Vec<T>::store(dx + dst, acc); else dx[dst] = from_f32<T>(acc[0]);
+  }
+}
+
+inline UpAxis make_axis(int I, int factor) {
+  UpAxis a;
+  a.I = I; a.O = I * factor;
+  a.ratio = a.O > 1 ? (float)(I - 1) / (float)(a.O - 1) : 0.f;
+  return a;
+}
+
 // ---- weight packing: dst = permute(flip(src)) of a 5-D fp32 tensor, cast to the destination type, one launch ---------------------
 struct Perm5 { int dims[5]; int perm[5]; int flip; };
 template <typename T>
@@ -805,6 +910,36 @@ int ich_bn_act_bwd_drop(const void* dz, int dz_ld, const void* y, int y_ld, cons
   ICH_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, "ich_bn_act_bwd_drop: dropout probability %g outside [0, 1]", (double)drop_p);
   return bn_act_bwd_impl(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, dtype, M, C, relu, training,
                          make_drop(drop_p, (unsigned long long)seed), (cudaStream_t)stream, "ich_bn_act_bwd_drop");
+}
+
+int ich_upsample2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(FD == 1 || FD == 2, "ich_upsample2_fwd: depth factor %d (1 = 2-D, 2 = 3-D)", FD);
+  if ((long long)N * D * H * W * C == 0) return 0;
+  const UpAxis ad = make_axis(D, FD), ah = make_axis(H, 2), aw = make_axis(W, 2);
+  const long long out_vox = (long long)N * ad.O * ah.O * aw.O;
+  DISPATCH_T(dtype, "ich_upsample2_fwd", {
+    if (vec_ok<T>(x, x_ld, C) && vec_ok<T>(y, y_ld, C))
+      upsample2_fwd_kernel<T, true><<<grid_for(out_vox * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, ad, ah, aw, C);
+    else
+      upsample2_fwd_kernel<T, false><<<grid_for(out_vox * C, 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, ad, ah, aw, C);
+  })
+  return ich_check_launch("ich_upsample2_fwd");
+}
+
+int ich_upsample2_bwd(const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(FD == 1 || FD == 2, "ich_upsample2_bwd: depth factor %d (1 = 2-D, 2 = 3-D)", FD);
+  if ((long long)N * D * H * W * C == 0) return 0;
+  const UpAxis ad = make_axis(D, FD), ah = make_axis(H, 2), aw = make_axis(W, 2);
+  const long long in_vox = (long long)N * D * H * W;
+  DISPATCH_T(dtype, "ich_upsample2_bwd", {
+    if (vec_ok<T>(dy, dy_ld, C) && vec_ok<T>(dx, dx_ld, C))
+      upsample2_bwd_kernel<T, true><<<grid_for(in_vox * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, N, ad, ah, aw, C);
+    else
+      upsample2_bwd_kernel<T, false><<<grid_for(in_vox * C, 256), 256, 0, s>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, N, ad, ah, aw, C);
+  })
+  return ich_check_launch("ich_upsample2_bwd");
 }
 
 int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {

@@ -565,6 +565,41 @@ class UpConvCat(Function):
         return dx, dres, dw, db, None, None
 
 
+class UpsampleCat(Function):
+    """bilinear=True decoder stage (models/networks/UNet.py:69-72,117-119): nn.Upsample(scale_factor=2, tri/bilinear,
+    align_corners=True) written straight into its channel slab of torch.cat([res, up], 1)."""
+
+    @staticmethod
+    def forward(ctx, x, res, fd):
+        n, d, h, w, c = x.shape
+        cres = res.shape[-1]
+        ctot = cres + c
+        oshape = (n, d * fd, h * 2, w * 2, ctot)
+        if tuple(res.shape[:4]) != oshape[:4]:
+            raise RuntimeError(f'ich_b200: skip tensor {tuple(res.shape)} does not match the up-sampled grid {oshape}')
+        out = torch.empty(oshape, dtype=x.dtype, device=x.device)
+        m_out = oshape[0] * oshape[1] * oshape[2] * oshape[3]
+        rp, rld = _rows(res)
+        call('ich_slab_copy', rp, rld, out.data_ptr(), ctot, _dt(x), m_out, cres, _stream())
+        up = out[..., cres:]
+        xp, xld = _rows(x)
+        call('ich_upsample2_fwd', xp, xld, up.data_ptr(), ctot, _dt(x), n, d, h, w, c, fd, _stream())
+        ctx.geom = (n, d, h, w, c, cres, fd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, d, h, w, c, cres, fd = ctx.geom
+        dout = dout.contiguous()
+        ctot = dout.shape[-1]
+        need = ctx.needs_input_grad
+        dx = None
+        if need[0]:
+            dx = torch.empty((n, d, h, w, c), dtype=dout.dtype, device=dout.device)
+            call('ich_upsample2_bwd', dout[..., cres:].data_ptr(), ctot, dx.data_ptr(), c, _dt(dout), n, d, h, w, c, fd, _stream())
+        return dx, (dout[..., :cres] if need[1] else None), None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # final 1x1 conv + Sigmoid / Softmax / Identity (models/networks/UNet.py:84-91,122) -> fp32 NC(D)HW
 # ---------------------------------------------------------------------------------------------------------------

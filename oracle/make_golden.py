@@ -32,6 +32,29 @@ def grads_of(net):
     return {k: p.grad.clone() for k, p in net.named_parameters()}
 
 
+def bilinear_fixtures(ref_unet, ref_loss, UO, LO, report):
+    """bilinear=True decoders (reference UNet.py:69-72): 3-D trilinear and 2-D bilinear nets, ComboLoss, all gradients."""
+    cases = {}
+    for name, use_3D, shape, seed in [('3d', True, (2, 1, 8, 16, 16), 21), ('2d', False, (2, 1, 32, 32), 22)]:
+        torch.manual_seed(seed)
+        kw = dict(depth=3, use_3D=use_3D, bilinear=True, in_channels=1, out_channels=1, top_filter=8, midchannels_factor=2, p_dropout=0.0)
+        net = ref_unet.UNet(**kw).train()
+        g = torch.Generator().manual_seed(seed)
+        x = torch.rand(*shape, generator=g)
+        mask = (torch.rand(*shape, generator=g) > 0.9).float()
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        lk = dict(alpha=0.5, beta=0.5, reduction='mean', p=1)
+        out = net(x)
+        loss = ref_loss.ComboLoss(**lk)(out, mask)
+        loss.backward()
+        cases[name] = dict(kwargs=kw, x=x, mask=mask, state_dict=sd0, out_train=out.detach(), loss=loss.detach(), grads=grads_of(net),
+                           loss_kwargs=lk)
+        o = UO.unet_forward(x, sd0, use_3D=use_3D, training=True)
+        report[f'bilinear {name} out'] = (o - out).abs().max().item()
+        report[f'bilinear {name} loss'] = abs(LO.combo_loss(o, mask, **lk).item() - loss.item()) / abs(loss.item())
+    torch.save(cases, os.path.join(OUT, 'unet_bilinear.pt'))
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import unet_oracle as UO, losses_oracle as LO
@@ -39,6 +62,12 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
     report = {}
+    if '--bilinear-only' in sys.argv:      # add the bilinear fixtures without rewriting the others
+        bilinear_fixtures(ref_unet, ref_loss, UO, LO, report)
+        for k, v in report.items():
+            print(f'{k:60s} oracle-vs-reference {v:.3e}')
+        assert max(report.values()) < 5e-5
+        return
 
     # ---- 1. supervised 3-D U-Net + ComboLoss (cfg-1 graph, shrunk) ------------------------------------
     torch.manual_seed(0)
@@ -182,6 +211,8 @@ def main():
         np.random.seed(seed)
         report[f'LocalInfoNCE {bs,H,W,C}'] = abs(LO.local_info_nce_loss(f1.detach(), f2.detach(), tau, K, A).item() - v.item())
     torch.save(dict(pred=pred, mask=mask, cases=cases, infonce=nce, local=loc), os.path.join(OUT, 'losses.pt'))
+
+    bilinear_fixtures(ref_unet, ref_loss, UO, LO, report)
 
     worst = 0.0
     for k, v in report.items():

@@ -55,8 +55,10 @@ def _n_blocks(sd, name):
 
 
 def unet_forward(x, sd, use_3D=True, training=True, use_final_activation=True, return_bottleneck=False, new_stats=None):
-    """UNet.forward, models/networks/UNet.py:93-127 (ConvTranspose variant, bilinear=False)."""
+    """UNet.forward, models/networks/UNet.py:93-127.  bilinear=True nets (nn.Upsample(scale_factor=2, tri/bilinear,
+    align_corners=True) instead of ConvTranspose, :69-72) are recognised by the absence of up_samp weights in the state dict."""
     conv, convT, pool = _dims(use_3D)
+    bilinear = 'up_samp.0.weight' not in sd
     res = []
     for i in range(_n_blocks(sd, 'down_block')):                       # :106-109
         x = conv_block(x, sd, f'down_block.{i}', training, use_3D, new_stats)
@@ -64,8 +66,11 @@ def unet_forward(x, sd, use_3D=True, training=True, use_final_activation=True, r
         x = pool(x, kernel_size=2, stride=2)
     x = conv_block(x, sd, 'bottleneck_block', training, use_3D, new_stats)   # :112
     xb = x
-    for i, r in zip(range(_n_blocks(sd, 'up_samp')), res[::-1]):      # :117-119
-        x = convT(x, sd[f'up_samp.{i}.weight'], sd[f'up_samp.{i}.bias'], stride=2)
+    for i, r in zip(range(_n_blocks(sd, 'up_block')), res[::-1]):     # :117-119
+        if bilinear:
+            x = F.interpolate(x, scale_factor=2, mode='trilinear' if use_3D else 'bilinear', align_corners=True)
+        else:
+            x = convT(x, sd[f'up_samp.{i}.weight'], sd[f'up_samp.{i}.bias'], stride=2)
         x = conv_block(torch.cat([r, x], dim=1), sd, f'up_block.{i}', training, use_3D, new_stats)
     x = conv(x, sd['final_conv.weight'], sd['final_conv.bias'])        # :122
     if use_final_activation:                                            # :85-91

@@ -88,3 +88,21 @@ def test_sliding_window_identity():
     assert torch.equal(pred, whole) and torch.equal(mask, whole >= 0.5)
     pred2, _ = UO.sliding_window_predict(vol, fx_sd, (8, 8, 8), (8, 4, 4))
     assert pred2.shape == vol.shape and torch.isfinite(pred2).all()
+
+
+def test_bilinear_decoders(golden):
+    """bilinear=True nets (nn.Upsample align_corners=True, reference UNet.py:69-72): 3-D trilinear and 2-D bilinear."""
+    fxs = golden('unet_bilinear.pt')
+    for name, fx in fxs.items():
+        use_3D = fx['kwargs']['use_3D']
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in fx['state_dict'].items()}
+        out = UO.unet_forward(fx['x'], sd, use_3D=use_3D, training=True)
+        assert torch.allclose(out, fx['out_train'], atol=2e-6), name
+        loss = LO.combo_loss(out, fx['mask'], **fx['loss_kwargs'])
+        assert abs(loss.item() - fx['loss'].item()) <= 1e-5 * abs(fx['loss'].item())
+        loss.backward()
+        for k, g in fx['grads'].items():
+            if k.endswith('conv1.bias') or k.endswith('conv2.bias'):
+                continue
+            assert (sd[k].grad - g).norm() / (g.norm() + 1e-12) < 1e-3, (name, k)
+

@@ -375,6 +375,54 @@ def test_unet3d_end_to_end_fp32(golden):
         assert torch.equal((ev >= 0.5).cpu(), fx['out_eval'] >= 0.5)
 
 
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('fd', [2, 1])
+def test_upsample_cat(prec, fd):
+    """bilinear=True decoder stage: nn.Upsample(scale_factor=2, tri/bilinear, align_corners=True) + torch.cat([res, up], 1)
+    (reference UNet.py:69-72,117-119) against torch CPU, forward and both gradients; odd sizes and a size-1 axis included."""
+    for (n, d, h, w, c, cres) in [(2, 3, 5, 7, 16, 8), (1, 1, 4, 6, 3, 5), (1, 2, 8, 16, 32, 16)]:
+        if fd == 1:
+            d = 1
+        g = torch.Generator().manual_seed(n + d + h + w + c)
+        x = torch.randn(n, c, d, h, w, generator=g)
+        res = torch.randn(n, cres, d * fd, 2 * h, 2 * w, generator=g)
+        dout = torch.randn(n, cres + c, d * fd, 2 * h, 2 * w, generator=g)
+        if prec == 'bf16':
+            x, res, dout = x.bfloat16().float(), res.bfloat16().float(), dout.bfloat16().float()
+        xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        if fd == 2:
+            up = F.interpolate(xr, scale_factor=2, mode='trilinear', align_corners=True)
+        else:
+            up = F.interpolate(xr[:, :, 0], scale_factor=2, mode='bilinear', align_corners=True).unsqueeze(2)
+        outr = torch.cat([rr, up], 1)
+        outr.backward(dout)
+        with config.override(precision=prec):
+            dt = config.act_dtype()
+            xc, rc = cl(x, dt).requires_grad_(True), cl(res, dt).requires_grad_(True)
+            out = ops.UpsampleCat.apply(xc, rc, fd)
+            out.backward(cl(dout, dt))
+        tol = 1e-5 if prec == 'fp32' else 1e-2
+        assert rel(nc(out), outr) < tol
+        assert rel(nc(xc.grad), xr.grad) < tol and rel(nc(rc.grad), rr.grad) < tol
+
+
+@pytest.mark.parametrize('name', ['3d', '2d'])
+def test_bilinear_unet_end_to_end_fp32(golden, name):
+    """bilinear=True U-Nets (fp32 mode) against the golden runs of the unmodified reference."""
+    from src.models.networks.UNet import UNet
+    from src.models.optim.LossFunctions import ComboLoss
+    fx = golden('unet_bilinear.pt')[name]
+    with config.override(precision='fp32'):
+        net = _load(UNet, fx)
+        out = net(fx['x'].to(DEV).requires_grad_(True))
+        loss = ComboLoss(**fx['loss_kwargs'])(out, fx['mask'].to(DEV))
+        loss.backward()
+    assert rel(out, fx['out_train']) < 1e-4
+    assert abs(loss.item() - fx['loss'].item()) < 1e-4 * abs(fx['loss'].item())
+    assert torch.equal((out >= 0.5).cpu(), fx['out_train'] >= 0.5)
+    _grad_check(net, fx, 5e-3, 0.0)
+
+
 def test_zero_copy_concat_matches_copying_path(golden):
     """Optional layout (ICH_B200_ZERO_COPY_CONCAT=1): skip tensors written straight into the decoder's concat buffer must give
     the same forward / backward as the copying path (fp32 mode: identical kernels, identical values)."""
