@@ -36,7 +36,8 @@ struct Params {
 
 constexpr int STAGES = 2;        // weight-gradient kernel
 constexpr int MAX_STAGES = 8;    // forward kernel: runtime depth (2 for the big 3x3 slabs, up to 8 for the small 1x1 GEMM stages)
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 224;   // slab kernel: warp 0 TMA, warps 1 and 6 MMA issuers (even / odd tiles), warps 2..5 epilogue
+constexpr int F_ISSUERS = 2;
 constexpr int W_THREADS = 256;   // weight-gradient kernel: warp 0 TMA, warps 1 / 6 / 7 MMA issuers (one per accumulator group), warps 2..5 epilogue
 constexpr int W_ISSUERS = 3;
 
@@ -55,8 +56,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], F_ISSUERS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], F_ISSUERS); mbar_init(&tempty_bar[a], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -99,9 +100,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================== MMA issuer (warp-uniform loop, elected lane issues)
+  } else if (warp == 1 || warp == 6) {
+    // ===================================================== MMA issuers (warp-uniform loops, elected lane issues).  One warp's issue
+    // loop costs more cycles per MMA (~68) than an N <= 64 MMA itself (40-48, profiles/r01_mma_rate2.txt): two warps on different SM
+    // sub-partitions issue the even and the odd M tiles of every tap.
     {
+      const int ii = warp == 1 ? 0 : 1;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
       // The single issuing thread is the critical resource (measured: ~130 cycles per MMA when descriptors were rebuilt
       // from scratch): keep the per-MMA work to two adds + one register pack.  Descriptor = {lo: start>>4 | LBO, hi: const}.
@@ -140,13 +144,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
               for (int kw = 0; kw < KS; ++kw) {
                 const uint64_t bdesc = pack64(b_lo, desc_hi);
                 b_lo += btap16;
-                uint32_t a_lo = a_kh + 2u * (uint32_t)kw;
-                uint32_t dcol = d_tmem;
-#pragma unroll 4
-                for (int tt = 0; tt < T; ++tt) {
+                uint32_t a_lo = a_kh + 2u * (uint32_t)kw + (uint32_t)ii * tile16;
+                uint32_t dcol = d_tmem + (uint32_t)ii * NB;
+#pragma unroll 2
+                for (int tt = ii; tt < T; tt += F_ISSUERS) {
                   if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, idesc, accum);
-                  a_lo += tile16;
-                  dcol += NB;
+                  a_lo += F_ISSUERS * tile16;
+                  dcol += F_ISSUERS * NB;
                 }
                 accum = 1u;
               }
@@ -160,7 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ===================================================== epilogue warps (2..5): TMEM lane quadrant = warp % 4
     const int q = warp & 3;
     const int l = q * 32 + lane;
