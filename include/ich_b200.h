@@ -97,6 +97,8 @@ int ich_bn_finalize(const double* sum, const double* sumsq, long long count, int
                     float* save_mean, float* save_invstd, int training, void* stream);
 int ich_affine_act(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C, int relu,
                    void* stream);
+/* `sums` is a caller-provided workspace of ICH_BN_SUM_COPIES * 2 * C doubles (replicated partial sums, zeroed by the call) */
+#define ICH_BN_SUM_COPIES 16
 int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
                    const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype, long long M, int C, int relu,
                    int training, void* stream);

@@ -49,9 +49,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_stat[2][64];          // per-CTA BatchNorm partial sums (one global atomic per channel per CTA)
 
   // broadcast from lane 0 so the compiler KNOWS the role index is warp-uniform (uniform branches + uniform datapath)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (STATS && threadIdx.x < 128) s_stat[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
@@ -231,15 +233,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (STATS) {   // once per CTA: warp tree over the 32 voxel lanes, then one fp64 atomic per channel per warp
+    if (STATS) {   // once per CTA: warp tree over the 32 voxel lanes, shared-memory sums of the 4 warps, ONE fp64 atomic per channel
 #pragma unroll
       for (int k = 0; k < 64; ++k) {
-        if (k < p.NB) {
-          const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
-          if (lane == 0) {
-            atomicAdd(&p.stat_sum[nb_fixed * p.NB + k], (double)a);
-            atomicAdd(&p.stat_sumsq[nb_fixed * p.NB + k], (double)b);
-          }
+        const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
+        if (lane == 0) { atomicAdd(&s_stat[0][k], a); atomicAdd(&s_stat[1][k], b); }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2) {
+        for (int k = lane; k < p.NB; k += 32) {
+          atomicAdd(&p.stat_sum[nb_fixed * p.NB + k], (double)s_stat[0][k]);
+          atomicAdd(&p.stat_sumsq[nb_fixed * p.NB + k], (double)s_stat[1][k]);
         }
       }
     }

@@ -71,8 +71,10 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[S_MAX_STAGES], empty_bar[S_MAX_STAGES], tfull_bar[SLOTS], tempty_bar[SLOTS], w_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_stat[2][64];          // per-CTA BatchNorm partial sums (one global atomic per channel per CTA)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (STATS && threadIdx.x < 128) s_stat[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
@@ -325,15 +327,17 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       }
       g_base += dend - d0;
     }
-    if (STATS) {
+    if (STATS) {   // warp tree -> shared-memory sums of the 8 epilogue warps -> ONE fp64 atomic per channel per CTA
 #pragma unroll
       for (int k = 0; k < SNB; ++k) {
-        if (k < p.NB) {
-          const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
-          if (lane == 0) {
-            atomicAdd(&p.stat_sum[n0 + k], (double)a);
-            atomicAdd(&p.stat_sumsq[n0 + k], (double)b);
-          }
+        const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
+        if (lane == 0) { atomicAdd(&s_stat[0][k], a); atomicAdd(&s_stat[1][k], b); }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(S_EPI_WARPS * 32) : "memory");
+      if (warp == 4) {
+        for (int k = lane; k < p.NB; k += 32) {
+          atomicAdd(&p.stat_sum[n0 + k], (double)s_stat[0][k]);
+          atomicAdd(&p.stat_sumsq[n0 + k], (double)s_stat[1][k]);
         }
       }
     }

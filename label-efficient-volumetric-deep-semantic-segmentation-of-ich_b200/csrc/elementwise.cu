@@ -12,6 +12,16 @@ __host__ __device__ inline bool vec_ok(const void* p, int ld, int C) {
   return (C % Vec<T>::N == 0) && (ld % Vec<T>::N == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
 
+// The BN-backward partial sums are accumulated with fp64 atomics into BN_COPIES replicas of the [2][C] vector (replica = block %
+// BN_COPIES): ~1200 blocks finishing together on the same 2*C addresses cost 50-100 us per launch in serialised atomics.
+constexpr int BN_COPIES = 16;
+__device__ __forceinline__ double bn_total(const double* __restrict__ sums, int i, int C) {
+  double t = 0.0;
+#pragma unroll
+  for (int k = 0; k < BN_COPIES; ++k) t += sums[(size_t)k * 2 * C + i];
+  return t;
+}
+
 // ---- fused dropout (nn.Dropout after the second ReLU of a ConvBlock, reference models/networks/UNet.py:150,175-176) -------------
 // Counter-based: the keep decision of element (row r, channel c) is a pure function of (seed, r, c), so the forward kernel and the
 // two backward kernels regenerate the same mask and no mask tensor is ever stored.  One Philox4x32-10 block yields eight 16-bit
@@ -233,7 +243,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 }
 
 // ---- z = [relu](y * scale[c] + shift[c]) --------------------------------------------------------------------------
-template <typename T, bool VEC>
+template <typename T, bool VEC, bool DROP>
 __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, T* __restrict__ z, int z_ld, long long M, int C,
                                                          int relu, const Drop drop) {
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ y
       float t = fmaf(v[k], scale[c + k], shift[c + k]);
       v[k] = relu ? fmaxf(t, 0.f) : t;
     }
-    if (drop.thr) {
+    if (DROP) {
       float m[V];
       drop_mult<V>(drop, r, c, m);
 #pragma unroll
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ y
 
 // ---- BatchNorm(+ReLU) backward ------------------------------------------------------------------------------------
 // pass 1: dbeta[c] = sum g, dgamma[c] = sum g * xhat, g = dz * [y*scale+shift > 0]
-template <typename T, bool VEC>
+template <typename T, bool VEC, bool DROP>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
                                                             const float* __restrict__ scale, const float* __restrict__ shift,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd, long long M,
@@ -286,7 +296,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
       float a[V], b[V];
       if (VEC) { Vec<T>::load(dz + r * dz_ld + c, a); Vec<T>::load(y + r * y_ld + c, b); }
       else { a[0] = to_f32(dz[r * dz_ld + c]); b[0] = to_f32(y[r * y_ld + c]); }
-      if (drop.thr) {
+      if (DROP) {
         float m[V];
         drop_mult<V>(drop, r, c, m);
 #pragma unroll
@@ -306,11 +316,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += 256) atomicAdd(&sums[c], (double)sh[c]);
+  for (int c = threadIdx.x; c < 2 * C; c += 256) atomicAdd(&sums[(size_t)(blockIdx.x % BN_COPIES) * 2 * C + c], (double)sh[c]);
 }
 
 // pass 2: dy = scale * (g - dbeta/M - xhat * dgamma/M)   (training) ;  dy = scale * g  (eval)
-template <typename T, bool VEC>
+template <typename T, bool VEC, bool DROP>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -320,10 +330,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   const int groups = C / V;
   const long long total = M * groups;
   const float invM = training ? (float)(1.0 / (double)M) : 0.f;
+  extern __shared__ float tot[];   // [2][C]: the replicas summed once per block
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) tot[c] = (float)bn_total(sums, c, C);
+  __syncthreads();
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (float)sums[c];
-      if (dgamma) dgamma[c] = (float)sums[C + c];
+      if (dbeta) dbeta[c] = tot[c];
+      if (dgamma) dgamma[c] = tot[C + c];
     }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r = i / groups;
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     float a[V], b[V], o[V];
     if (VEC) { Vec<T>::load(dz + r * dz_ld + c, a); Vec<T>::load(y + r * y_ld + c, b); }
     else { a[0] = to_f32(dz[r * dz_ld + c]); b[0] = to_f32(y[r * y_ld + c]); }
-    if (drop.thr) {
+    if (DROP) {
       float m[V];
       drop_mult<V>(drop, r, c, m);
 #pragma unroll
@@ -342,7 +355,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
       float sc = scale[c + k];
       float gk = (!relu || fmaf(b[k], sc, shift[c + k]) > 0.f) ? a[k] : 0.f;
       float xhat = (b[k] - mean[c + k]) * invstd[c + k];
-      o[k] = sc * (gk - (float)sums[c + k] * invM - xhat * (float)sums[C + c + k] * invM);
+      o[k] = sc * (gk - tot[c + k] * invM - xhat * tot[C + c + k] * invM);
     }
     if (VEC) Vec<T>::store(dy + r * dy_ld + c, o); else dy[r * dy_ld + c] = from_f32<T>(o[0]);
   }
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 
 // ---- fast paths: C/V divides 256, so a thread owns ONE 16-byte channel group for the whole kernel (per-channel constants live
 //      in registers, no index division in the loop) and strides over rows with several independent loads in flight. ---------
-template <typename T>
+template <typename T, bool DROP>
 __global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, T* __restrict__ z, int z_ld, long long M, int C, int relu,
                                                               const Drop drop) {
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restric
       a[k] = fmaf(a[k], sc[k], sh[k]); b[k] = fmaf(b[k], sc[k], sh[k]);
       if (relu) { a[k] = fmaxf(a[k], 0.f); b[k] = fmaxf(b[k], 0.f); }
     }
-    if (drop.thr) {
+    if (DROP) {
       float m0[V], m1[V];
       drop_mult<V>(drop, r, c, m0); drop_mult<V>(drop, r + step, c, m1);
 #pragma unroll
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restric
     Vec<T>::load(y + r * y_ld + c, a);
 #pragma unroll
     for (int k = 0; k < V; ++k) { a[k] = fmaf(a[k], sc[k], sh[k]); if (relu) a[k] = fmaxf(a[k], 0.f); }
-    if (drop.thr) {
+    if (DROP) {
       float m0[V];
       drop_mult<V>(drop, r, c, m0);
 #pragma unroll
@@ -396,7 +409,7 @@ __global__ void __launch_bounds__(256) affine_act_rows_kernel(const T* __restric
   }
 }
 
-template <typename T>
+template <typename T, bool DROP>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
                                                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                                                  const float* __restrict__ mean, const float* __restrict__ invstd, long long M, int C,
@@ -414,7 +427,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
     float a[U][V], b[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) { Vec<T>::load(dz + (r + u * step) * dz_ld + c, a[u]); Vec<T>::load(y + (r + u * step) * y_ld + c, b[u]); }
-    if (drop.thr) {
+    if (DROP) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         float m[V];
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
   for (; r < M; r += step) {
     float a0[V], b0[V];
     Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
-    if (drop.thr) {
+    if (DROP) {
       float m[V];
       drop_mult<V>(drop, r, c, m);
 #pragma unroll
@@ -454,10 +467,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
 #pragma unroll
   for (int k = 0; k < V; ++k) { atomicAdd(&sh[c + k], sb[k]); atomicAdd(&sh[C + c + k], sg[k]); }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&sums[(size_t)(blockIdx.x % BN_COPIES) * 2 * C + i], (double)sh[i]);
 }
 
-template <typename T>
+template <typename T, bool DROP>
 __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restrict__ dz, int dz_ld, const T* __restrict__ y, int y_ld,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -468,18 +481,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
   const int groups = C / V, rpb = 256 / groups;
   const int c = (threadIdx.x % groups) * V;
   const float invM = training ? (float)(1.0 / (double)M) : 0.f;
+  extern __shared__ float tot[];   // [2][C]: the replicas summed once per block
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tot[i] = (float)bn_total(sums, i, C);
+  __syncthreads();
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
-      if (dbeta) dbeta[i] = (float)sums[i];
-      if (dgamma) dgamma[i] = (float)sums[C + i];
+      if (dbeta) dbeta[i] = tot[i];
+      if (dgamma) dgamma[i] = tot[C + i];
     }
   // dy = sc * g - k0 - y * k1  with  k1 = sc * is * dgamma/M,  k0 = sc * dbeta/M - mu * k1
   float sc[V], sf[V], k0[V], k1[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     sc[k] = scale[c + k]; sf[k] = shift[c + k];
-    k1[k] = sc[k] * invstd[c + k] * (float)sums[C + c + k] * invM;
-    k0[k] = sc[k] * (float)sums[c + k] * invM - mean[c + k] * k1[k];
+    k1[k] = sc[k] * invstd[c + k] * tot[C + c + k] * invM;
+    k0[k] = sc[k] * tot[c + k] * invM - mean[c + k] * k1[k];
   }
   const long long step = (long long)gridDim.x * rpb;
   long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
@@ -487,7 +503,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
     float a0[V], b0[V], a1[V], b1[V];
     Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
     Vec<T>::load(dz + (r + step) * dz_ld + c, a1); Vec<T>::load(y + (r + step) * y_ld + c, b1);
-    if (drop.thr) {
+    if (DROP) {
       float m0[V], m1[V];
       drop_mult<V>(drop, r, c, m0); drop_mult<V>(drop, r + step, c, m1);
 #pragma unroll
@@ -506,7 +522,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
   if (r < M) {
     float a0[V], b0[V];
     Vec<T>::load(dz + r * dz_ld + c, a0); Vec<T>::load(y + r * y_ld + c, b0);
-    if (drop.thr) {
+    if (DROP) {
       float m0[V];
       drop_mult<V>(drop, r, c, m0);
 #pragma unroll
@@ -794,6 +810,38 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 
 }  // namespace
 
+template <typename T, bool DROPV>
+static void affine_act_launch(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, long long M, int C, int relu,
+                              const Drop drop, cudaStream_t s) {
+  if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C) && rows_fast_ok(C, Vec<T>::N))
+    affine_act_rows_kernel<T, DROPV><<<rows_grid(M, C, Vec<T>::N), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
+  else if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C))
+    affine_act_kernel<T, true, DROPV><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
+  else
+    affine_act_kernel<T, false, DROPV><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
+}
+
+template <typename T, bool DROPV>
+static void bn_act_bwd_launch(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                              const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, long long M, int C, int relu,
+                              int training, const Drop drop, cudaStream_t s) {
+  const int rows_per_block = 2048;
+  unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
+  size_t shbytes = sizeof(float) * 2 * C;
+  bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
+  if (vec && rows_fast_ok(C, Vec<T>::N)) {
+    const int grid = rows_grid(M, C, Vec<T>::N);
+    bn_bwd_reduce_rows_kernel<T, DROPV><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
+    bn_bwd_apply_rows_kernel<T, DROPV><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
+  } else if (vec) {
+    bn_bwd_reduce_kernel<T, true, DROPV><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
+    bn_bwd_apply_kernel<T, true, DROPV><<<grid_for(M * (C / Vec<T>::N), 256), 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
+  } else {
+    bn_bwd_reduce_kernel<T, false, DROPV><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
+    bn_bwd_apply_kernel<T, false, DROPV><<<grid_for(M * C, 256), 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
+  }
+}
+
 #define DISPATCH_T(dtype, what, ...)                                   \
   if (dtype == ICH_F32) { typedef float T; __VA_ARGS__ }               \
   else if (dtype == ICH_BF16) { typedef bf16 T; __VA_ARGS__ }          \
@@ -849,13 +897,11 @@ int ich_bn_finalize(const double* sum, const double* sumsq, long long count, int
 static int affine_act_impl(const void* y, int y_ld, const float* scale, const float* shift, void* z, int z_ld, int dtype, long long M, int C,
                            int relu, const Drop drop, cudaStream_t s, const char* what) {
   if (M * C == 0) return 0;
+  // the dropout variants are separate instantiations: the Philox code costs ~50 registers, which halves the occupancy of the
+  // (bandwidth-bound) plain kernels if it is merely branched around
   DISPATCH_T(dtype, what, {
-    if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C) && rows_fast_ok(C, Vec<T>::N))
-      affine_act_rows_kernel<T><<<rows_grid(M, C, Vec<T>::N), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
-    else if (vec_ok<T>(y, y_ld, C) && vec_ok<T>(z, z_ld, C))
-      affine_act_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
-    else
-      affine_act_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)y, y_ld, scale, shift, (T*)z, z_ld, M, C, relu, drop);
+    if (drop.thr) affine_act_launch<T, true>(y, y_ld, scale, shift, z, z_ld, M, C, relu, drop, s);
+    else affine_act_launch<T, false>(y, y_ld, scale, shift, z, z_ld, M, C, relu, drop, s);
   })
   return ich_check_launch(what);
 }
@@ -873,39 +919,26 @@ int ich_affine_act_drop(const void* y, int y_ld, const float* scale, const float
 }
 
 static int bn_act_bwd_impl(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
-                           const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                           const float* invstd, double* sums /*[ICH_BN_SUM_COPIES*2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
                            long long M, int C, int relu, int training, const Drop drop, cudaStream_t s, const char* what) {
   if (M * C == 0) return 0;
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
-  const int rows_per_block = 2048;
-  unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
-  size_t shbytes = sizeof(float) * 2 * C;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * BN_COPIES, s);
   DISPATCH_T(dtype, what, {
-    bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
-    if (vec && rows_fast_ok(C, Vec<T>::N)) {
-      const int grid = rows_grid(M, C, Vec<T>::N);
-      bn_bwd_reduce_rows_kernel<T><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
-      bn_bwd_apply_rows_kernel<T><<<grid, 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
-    } else if (vec) {
-      bn_bwd_reduce_kernel<T, true><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
-      bn_bwd_apply_kernel<T, true><<<grid_for(M * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
-    } else {
-      bn_bwd_reduce_kernel<T, false><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
-      bn_bwd_apply_kernel<T, false><<<grid_for(M * C, 256), 256, 0, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
-    }
+    if (drop.thr) bn_act_bwd_launch<T, true>(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, M, C, relu, training, drop, s);
+    else bn_act_bwd_launch<T, false>(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, M, C, relu, training, drop, s);
   })
   return ich_check_launch(what);
 }
 
 int ich_bn_act_bwd(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
-                   const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                   const float* invstd, double* sums /*[ICH_BN_SUM_COPIES*2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
                    long long M, int C, int relu, int training, void* stream) {
   return bn_act_bwd_impl(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, dtype, M, C, relu, training,
                          make_drop(0.f, 0), (cudaStream_t)stream, "ich_bn_act_bwd");
 }
 
 int ich_bn_act_bwd_drop(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
-                        const float* invstd, double* sums /*[2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                        const float* invstd, double* sums /*[ICH_BN_SUM_COPIES*2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
                         long long M, int C, int relu, int training, float drop_p, long long seed, void* stream) {
   ICH_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, "ich_bn_act_bwd_drop: dropout probability %g outside [0, 1]", (double)drop_p);
   return bn_act_bwd_impl(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, dtype, M, C, relu, training,

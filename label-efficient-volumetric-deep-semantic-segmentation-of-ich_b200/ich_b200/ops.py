@@ -9,6 +9,7 @@ from ._lib import call
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
+BN_SUM_COPIES = 16      # ICH_BN_SUM_COPIES of include/ich_b200.h: replicated partial sums of the BN-backward reduction
 
 
 def _stream():
@@ -365,7 +366,7 @@ class ConvBnRelu(Function):
             dz = dz.contiguous()
             dzp, dzld = dz.data_ptr(), cout
         dy = torch.empty_like(y)
-        sums = torch.empty((2, cout), dtype=torch.float64, device=y.device)
+        sums = torch.empty((BN_SUM_COPIES * 2, cout), dtype=torch.float64, device=y.device)
         dgamma = torch.empty(cout, dtype=torch.float32, device=y.device)
         dbeta = torch.empty(cout, dtype=torch.float32, device=y.device)
         if ctx.drop[0] > 0.0:
@@ -409,7 +410,7 @@ class ConvBias(Function):
             stats = torch.zeros((4, cout), dtype=torch.float32, device=dev)
             stats[0].fill_(1.0)
             stats[3].fill_(1.0)
-            sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
+            sums = torch.empty((BN_SUM_COPIES * 2, cout), dtype=torch.float64, device=dev)
             dy = torch.empty_like(z)
             db = torch.empty(cout, dtype=torch.float32, device=dev)
             call('ich_bn_act_bwd', dz.data_ptr(), cout, z.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
