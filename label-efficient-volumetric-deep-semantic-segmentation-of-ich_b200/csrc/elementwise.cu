@@ -461,13 +461,37 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_rows_kernel(const T* __rest
       sg[k] = fmaf(g0, (b0[k] - mu[k]) * is[k], sg[k]);
     }
   }
-  extern __shared__ float sh[];  // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
-  __syncthreads();
+  // block reduction without shared-memory atomics (64-way contended float atomics cost ~25 us per launch): lanes that own the same
+  // channel group are `groups` apart -> butterfly over those lanes, one row of partials per warp, then a sum over the 8 warps
+  extern __shared__ float sh[];  // [8 warps][2][C]
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < V; ++k) { atomicAdd(&sh[c + k], sb[k]); atomicAdd(&sh[C + c + k], sg[k]); }
+  for (int k = 0; k < V; ++k) {
+    for (int o = groups; o < 32; o <<= 1) {
+      sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], o);
+      sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], o);
+    }
+  }
+  if (groups >= 32 || lane < groups) {
+    // groups >= 32: every lane owns a distinct channel group and a warp covers only 32 of the groups; the final sum below reads
+    // exactly the warps that own a channel (the other slots are never written nor read)
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sh[(wrp * 2) * C + c + k] = sb[k]; sh[(wrp * 2 + 1) * C + c + k] = sg[k]; }
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&sums[(size_t)(blockIdx.x % BN_COPIES) * 2 * C + i], (double)sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float t = 0.f;
+    if (groups >= 32) {
+      // channel i % C belongs to group (i % C) / V, owned by the warps w with (w * 32 + lane) % groups == group
+      const int g = (i % C) / V;
+      for (int w = 0; w < 8; ++w)
+        if (((w * 32) % groups) <= g && g < ((w * 32) % groups) + 32) t += sh[(w * 2 + i / C) * C + (i % C)];
+    } else {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sh[(w * 2 + i / C) * C + (i % C)];
+    }
+    atomicAdd(&sums[(size_t)(blockIdx.x % BN_COPIES) * 2 * C + i], (double)t);
+  }
 }
 
 template <typename T, bool DROP>
@@ -831,7 +855,7 @@ static void bn_act_bwd_launch(const void* dz, int dz_ld, const void* y, int y_ld
   bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
   if (vec && rows_fast_ok(C, Vec<T>::N)) {
     const int grid = rows_grid(M, C, Vec<T>::N);
-    bn_bwd_reduce_rows_kernel<T, DROPV><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
+    bn_bwd_reduce_rows_kernel<T, DROPV><<<grid, 256, 8 * shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
     bn_bwd_apply_rows_kernel<T, DROPV><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
   } else if (vec) {
     bn_bwd_reduce_kernel<T, true, DROPV><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
