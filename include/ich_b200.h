@@ -80,6 +80,9 @@ int ich_convT2_tc_wgrad(const void* x, int x_ld, const void* g, int g_ld, float*
                         void* stream);
 /* fine grid [2x voxels][C] (pitch src_ld) -> coarse grid [voxel][tap*C + c], tap = (i<<2)|(j<<1)|l; backward of ConvTranspose k2 s2 */
 int ich_space_to_depth2(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
+/* same, also accumulating colsum[c] (fp64, zeroed here) = sum over all fine voxels of src[.][c] = the ConvTranspose bias gradient */
+int ich_space_to_depth2_sum(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, double* colsum,
+                            void* stream);
 
 /* ---- transposed conv k2 s2: nn.ConvTranspose3d/2d (models/networks/UNet.py:75-76). Grid args = the COARSE grid;
  *      FD = depth factor (2 for 3-D, 1 for 2-D). wpack = [Cin][taps*Cout], wpack_d = [taps*Cout][Cin], taps = 4*FD.     */

@@ -661,10 +661,15 @@ __global__ void __launch_bounds__(256) slab_copy_kernel(const T* __restrict__ sr
 // ---- space-to-depth (2x; depth factor FD): fine [N][FD*D][2H][2W][C] (pitch ld) -> coarse [N][D][H][W][taps*C] --------------
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) space_to_depth_kernel(const T* __restrict__ src, int s_ld, T* __restrict__ dst, int N, int D, int H, int W, int C,
-                                                             int FD) {
+                                                             int FD, double* __restrict__ colsum) {
   constexpr int V = VEC ? Vec<T>::N : 1;
   const int groups = C / V, taps = 4 * FD;
   const long long total = (long long)N * D * H * W * taps * groups;
+  // optional per-channel sum of everything copied (= the ConvTranspose bias gradient, reference UNet.py:75-76): the host only asks
+  // for it when 256 % groups == 0, so a thread keeps ONE channel group over its whole grid-stride loop
+  float cs[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) cs[k] = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int g = (int)(i % groups); long long t = i / groups;
     int tap = (int)(t % taps); t /= taps;            // t = coarse voxel
@@ -674,8 +679,40 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const T* __restrict
     long long fine = ((r * FD + ti) * (2 * H) + (2 * h + tj)) * (2LL * W) + (2 * w + tl);
     const T* sp = src + fine * s_ld + g * V;
     T* dp = dst + (t * taps + tap) * (long long)C + g * V;
-    if (VEC) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
-    else *dp = *sp;
+    if (VEC) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(sp);
+      *reinterpret_cast<uint4*>(dp) = raw;
+      if (colsum) {
+        float v[V];
+        Vec<T>::load(reinterpret_cast<const T*>(&raw), v);
+#pragma unroll
+        for (int k = 0; k < V; ++k) cs[k] += v[k];
+      }
+    } else {
+      *dp = *sp;
+      if (colsum) cs[0] += to_f32(*sp);
+    }
+  }
+  if (colsum) {
+    // lanes `groups` apart own the same channels: butterfly, per-warp partials, block sum, one fp64 atomic per channel per block
+    __shared__ float part[8][256];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, g = threadIdx.x % groups;
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      for (int o = groups; o < 32; o <<= 1) cs[k] += __shfl_xor_sync(0xffffffffu, cs[k], o);
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) part[i >> 8][i & 255] = 0.f;
+    __syncthreads();
+    if (groups >= 32 || lane < groups) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) part[wrp][g * V + k] = cs[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][c];
+      atomicAdd(&colsum[c], (double)t);
+    }
   }
 }
 
@@ -1040,18 +1077,32 @@ int ich_slab_copy(const void* src, int src_ld, void* dst, int dst_ld, int dtype,
   return ich_check_launch("ich_slab_copy");
 }
 
-int ich_space_to_depth2(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  ICH_REQUIRE(FD == 1 || FD == 2, "ich_space_to_depth2: FD must be 1 or 2");
+static int space_to_depth_impl(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, double* colsum,
+                               cudaStream_t s, const char* what) {
+  ICH_REQUIRE(FD == 1 || FD == 2, "%s: FD must be 1 or 2", what);
   long long total = (long long)N * D * H * W * 4 * FD * C;
+  if (colsum) cudaMemsetAsync(colsum, 0, sizeof(double) * C, s);
   if (total == 0) return 0;
-  DISPATCH_T(dtype, "ich_space_to_depth2", {
-    if (vec_ok<T>(src, src_ld, C) && vec_ok<T>(dst, C, C))
-      space_to_depth_kernel<T, true><<<grid_for(total / Vec<T>::N, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, N, D, H, W, C, FD);
+  DISPATCH_T(dtype, what, {
+    const bool vec = vec_ok<T>(src, src_ld, C) && vec_ok<T>(dst, C, C);
+    const int groups = vec ? C / Vec<T>::N : C;
+    ICH_REQUIRE(!colsum || (C <= 256 && groups <= 256 && 256 % groups == 0), "%s: fused channel sums need C / vector width to divide 256 (C = %d)", what, C);
+    if (vec)
+      space_to_depth_kernel<T, true><<<grid_for(total / Vec<T>::N, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, N, D, H, W, C, FD, colsum);
     else
-      space_to_depth_kernel<T, false><<<grid_for(total, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, N, D, H, W, C, FD);
+      space_to_depth_kernel<T, false><<<grid_for(total, 256), 256, 0, s>>>((const T*)src, src_ld, (T*)dst, N, D, H, W, C, FD, colsum);
   })
-  return ich_check_launch("ich_space_to_depth2");
+  return ich_check_launch(what);
+}
+
+int ich_space_to_depth2(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
+  return space_to_depth_impl(src, src_ld, dst, dtype, N, D, H, W, C, FD, nullptr, (cudaStream_t)stream, "ich_space_to_depth2");
+}
+
+int ich_space_to_depth2_sum(const void* src, int src_ld, void* dst, int dtype, int N, int D, int H, int W, int C, int FD, double* colsum,
+                            void* stream) {
+  ICH_REQUIRE(colsum != nullptr, "ich_space_to_depth2_sum: colsum is required");
+  return space_to_depth_impl(src, src_ld, dst, dtype, N, D, H, W, C, FD, colsum, (cudaStream_t)stream, "ich_space_to_depth2_sum");
 }
 
 int ich_permute5(const float* src, void* dst, int dtype, int d0, int d1, int d2, int d3, int d4, int p0, int p1, int p2, int p3, int p4,

@@ -541,7 +541,13 @@ class UpConvCat(Function):
             # re-pack the up-sampled gradient to the coarse grid once ([voxel][tap*Cout + co]); both gradients are then 1x1 GEMMs
             taps = 4 * fd
             g = torch.empty((n, d, h, w, taps * cout), dtype=dout.dtype, device=dout.device)
-            call('ich_space_to_depth2', dup.data_ptr(), ctot, g.data_ptr(), _dt(dout), n, d, h, w, cout, fd, _stream())
+            if need[3] and cout <= 256 and 256 % max(1, cout // 8) == 0 and cout % 8 == 0:
+                # the bias gradient (sum of the up-sampled gradient over voxels) rides along with the re-pack
+                bsum = torch.empty(cout, dtype=torch.float64, device=x.device)
+                call('ich_space_to_depth2_sum', dup.data_ptr(), ctot, g.data_ptr(), _dt(dout), n, d, h, w, cout, fd, bsum.data_ptr(), _stream())
+                db = bsum.float()
+            else:
+                call('ich_space_to_depth2', dup.data_ptr(), ctot, g.data_ptr(), _dt(dout), n, d, h, w, cout, fd, _stream())
             if need[0]:
                 dx = torch.empty_like(x)
                 call('ich_conv_tc_fwd', g.data_ptr(), taps * cout, _p(_pack(weight, 'convT_dgrad_tc')), None, dx.data_ptr(), cin, n, d, h, w,
@@ -550,7 +556,7 @@ class UpConvCat(Function):
                 dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
                 xp, xld = _rows(x)
                 call('ich_convT2_tc_wgrad', xp, xld, g.data_ptr(), taps * cout, dw.data_ptr(), n, d, h, w, cin, cout, fd, _stream())
-            need = (False, need[1], False, need[3], need[4])
+            need = (False, need[1], False, need[3] and db is None, need[4])
         if need[0]:
             dx = torch.empty_like(x)
             call('ich_convT2_dgrad', dup.data_ptr(), ctot, _p(_pack(weight, 'convT_dgrad')), dx.data_ptr(), cin, _dt(x), n, d, h, w, cin, cout,
