@@ -477,6 +477,7 @@ struct WParams {
   int kwf;                           // kw-fold: the three kw taps are the N dimension (N = 3 * 32): dy lands as 64-byte rows WITH a column halo and
                                      // MN block j of the B operand is the same tile shifted by j positions (LBO = one row) -> 3 MMAs per K step
   uint32_t a_off, b_off;             // operand offsets inside a stage
+  int bu;                            // dy tile rows (non-kw-fold modes): 16-byte units per position = 2 (16 ch, SWIZZLE_32B), 4 (32 ch, 64B), 8 (64 ch, 128B)
   int a64;                           // x slab as 64-byte SWIZZLE_64B rows (32-channel blocks) instead of 32-byte rows: half the TMA requests
   int WB, PW, R, RB, CU, NB, chunks_u, chunks_v;
   int n_wb, n_rb, n_cb, n_nb;
@@ -543,7 +544,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2 + khf, cb * (p.CU / (p.a64 ? 32 : 16)), coord);
           }
           if (p.kwf) tma_load_4d(sb, &map_dy, &full_bar[stage], nb * 32, w0 - 1, h0, n * p.D + d);
-          else tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / 16), n * p.D + d);
+          else tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / (8 * p.bu)), n * p.D + d);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -563,9 +564,11 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);
       const uint32_t AU = p.a64 ? 4u : 2u;                                         // 16-byte units per x position
       const uint32_t a_lbo = (((uint32_t)p.RB * p.PW * 16u * AU) >> 4) << 16;      // channel-block stride (16 or 32 channels per block)
-      const uint32_t b_lbo = (((uint32_t)p.R * p.WB * 32u) >> 4) << 16;
-      const uint32_t a_hi = p.a64 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi, b_hi = desc_hi;
-      const uint32_t PW = AU * (uint32_t)p.PW, WB = 2u * (uint32_t)p.WB, NB = (uint32_t)p.NB;   // row pitches in 16-byte units
+      const uint32_t BU = (uint32_t)p.bu;                                          // 16-byte units per dy position
+      const uint32_t b_lbo = (((uint32_t)p.R * p.WB * 16u * BU) >> 4) << 16;       // channel-block stride (16 / 32 / 64 channels per block)
+      const uint32_t a_hi = p.a64 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
+      const uint32_t b_hi = BU == 8 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : BU == 4 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
+      const uint32_t PW = AU * (uint32_t)p.PW, WB = BU * (uint32_t)p.WB, NB = (uint32_t)p.NB;   // row pitches in 16-byte units
       int stage = 0; uint32_t phase = 0;
       uint32_t accum = 0u;
       for (long long item = it_begin; item < it_end; ++item) {
@@ -591,9 +594,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           }
         } else
         for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, b_row += WB) {
-          for (uint32_t s16 = 0; s16 < WB; s16 += 32) {                            // 16 positions per MMA
-            const uint64_t bdesc = pack64(b_row + s16, b_hi);
-            const uint32_t a_s = a_row + (s16 >> 1) * AU;
+          for (uint32_t s = 0; s < (uint32_t)p.WB; s += 16) {                      // 16 positions per MMA
+            const uint64_t bdesc = pack64(b_row + BU * s, b_hi);
+            const uint32_t a_s = a_row + AU * s;
             if (KS == 1) {                 // 1x1 GEMM: one accumulator
               if (ii == 0 && elect_one()) umma_bf16(tmem_base, pack64(a_s, a_hi), bdesc, idesc, accum);
             } else if (khn == 1) {         // kh-split: accumulators = kw, this issuer's is kw = ii
@@ -694,7 +697,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
       if (((CU / 16) * RB * pw) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
       size_t a = (size_t)KD * chunks_u * RB * pw * 16;
       size_t b = kwf ? (size_t)R * (wb + 2) * 64 : (size_t)chunks_v * R * wb * 16;
-      size_t stage = (a + b + 1023) & ~(size_t)1023;
+      size_t stage = ((a + 1023) & ~(size_t)1023) + ((b + 1023) & ~(size_t)1023);   // both operand tiles start 1024-byte aligned
       // the MMA always reads 16 chunks (128 rows): chunks beyond KD*chunks_u are garbage rows, but must stay inside the allocation
       size_t over = (size_t)(16 - KD * chunks_u > 0 ? 16 - KD * chunks_u : 0) * RB * pw * 16 + (size_t)(2 * pw + 32) * 16;
       size_t total = STAGES * stage + over + 1024;
@@ -712,13 +715,15 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   p.plane_bytes = (uint32_t)chunks_u * p.RB * PW * 16u;
   p.a_bytes = (uint32_t)KD * p.plane_bytes;
   p.b_bytes = kwf ? (uint32_t)bestR * (WB + 2) * 64u : (uint32_t)chunks_v * bestR * WB * 16u;
-  p.stage_bytes = (uint32_t)(((size_t)p.a_bytes + p.b_bytes + 1023) & ~(size_t)1023);
+  p.stage_bytes = (uint32_t)((((size_t)p.a_bytes + 1023) & ~(size_t)1023) + (((size_t)p.b_bytes + 1023) & ~(size_t)1023));
   p.kwf = kwf ? 1 : 0;
+  { static int b64_env = -1; if (b64_env < 0) { const char* e = getenv("ICH_TC_WGRAD_B64"); b64_env = e ? atoi(e) : 1; }
+    p.bu = (b64_env && NB % 64 == 0) ? 8 : (b64_env && NB % 32 == 0) ? 4 : 2; }
   { static int a64_env = -1; if (a64_env < 0) { const char* e = getenv("ICH_TC_WGRAD_A64"); a64_env = e ? atoi(e) : 1; }
     p.a64 = (a64_env && CU % 32 == 0) ? 1 : 0; }
   // kw-fold: the 64-byte-swizzled dy tile sits at the (1024-byte aligned) stage base, the x planes follow it
   p.a_off = kwf ? p.b_bytes : 0u;
-  p.b_off = kwf ? 0u : p.a_bytes;
+  p.b_off = kwf ? 0u : (uint32_t)(((size_t)p.a_bytes + 1023) & ~(size_t)1023);   // dy tile (32 / 64 / 128-byte swizzled rows) 1024-byte aligned
   uint32_t cols = 32;
   while (cols < (uint32_t)((khs ? KS : KS * KS) * NB)) cols <<= 1;
   p.tmem_cols = cols;
@@ -775,11 +780,13 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy, kw-fold) failed with %d", what, (int)r);
   } else {
-    cuuint64_t dims[5] = {16, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 16), (cuuint64_t)N * D};
-    cuuint64_t strides[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, 32, (cuuint64_t)H * W * dy_ld * 2};
-    cuuint32_t box[5] = {16, (cuuint32_t)p.WB, (cuuint32_t)p.R, (cuuint32_t)(p.NB / 16), 1};
+    const cuuint32_t cbk = 8u * (cuuint32_t)p.bu;     // channels per block = one swizzled row (16 / 32 / 64)
+    cuuint64_t dims[5] = {cbk, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / cbk), (cuuint64_t)N * D};
+    cuuint64_t strides[4] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, 2ull * cbk, (cuuint64_t)H * W * dy_ld * 2};
+    cuuint32_t box[5] = {cbk, (cuuint32_t)p.WB, (cuuint32_t)p.R, (cuuint32_t)(p.NB / cbk), 1};
     CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     p.bu == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : p.bu == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy) failed with %d", what, (int)r);
   }
   static bool attr_set = false;
