@@ -543,7 +543,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const int coord = (dd < 0 || dd >= p.D) ? -1 : n * p.D + dd;    // -1: out of range -> the whole plane is zero-filled
             tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2 + khf, cb * (p.CU / (p.a64 ? 32 : 16)), coord);
           }
-          if (p.kwf) tma_load_4d(sb, &map_dy, &full_bar[stage], nb * 32, w0 - 1, h0, n * p.D + d);
+          if (p.kwf) tma_load_4d(sb, &map_dy, &full_bar[stage], nb * p.NB, w0 - 1, h0, n * p.D + d);
           else tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / (8 * p.bu)), n * p.D + d);
         }
         __syncwarp();
@@ -581,12 +581,15 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         if (p.kwf) {
           // B = dy slab [row][WB + 2 positions][32 co] as 64-byte SWIZZLE_64B rows; MN block j (32 columns) = the tile shifted by j
           // positions (LBO = 64 B), i.e. dy[q + j - 1] for x position q: column block j is kernel column kw = 2 - j.
-          const uint32_t kb_hi = (512u >> 4) | (1u << 14) | (4u << 29);
-          uint32_t bk_row = (((st + p.b_off) & 0x3FFFFu) >> 4) | ((64u >> 4) << 16);
-          const uint32_t BW = 4u * (uint32_t)(p.WB + 2);                           // dy row pitch in 16-byte units
-          for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, bk_row += BW) {
+          // NB = 64: the same with 128-byte SWIZZLE_128B rows (LBO = 128 B), N = 192, one kernel row per CTA (kh-split).
+          const uint32_t KU = NB >> 3;                                             // 16-byte units per dy position: 4 (NB = 32) or 8 (NB = 64)
+          const uint32_t kb_hi = KU == 8 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((512u >> 4) | (1u << 14) | (4u << 29));
+          uint32_t bk_row = (((st + p.b_off) & 0x3FFFFu) >> 4) | (KU << 16);       // LBO = one position
+          const uint32_t BW = KU * (uint32_t)(p.WB + 2);                           // dy row pitch in 16-byte units
+          const bool mine = ii < khn;                                              // kh-split: a single accumulator (issuer 0)
+          for (int r = 0; r < p.R && !(p.dbg & 1) && mine; ++r, a_row += PW, bk_row += BW) {
             for (uint32_t s = 0; s < (uint32_t)p.WB; s += 16) {                    // 16 positions per MMA
-              const uint64_t bdesc = pack64(bk_row + 4u * s, kb_hi);
+              const uint64_t bdesc = pack64(bk_row + KU * s, kb_hi);
               const uint32_t a_kh = a_row + AU * s + AU + (uint32_t)ii * PW;       // x position q = s (skip the halo column), kernel row ii
               if (elect_one()) umma_bf16(tmem_base + (uint32_t)ii * 3u * NB, pack64(a_kh, a_hi), bdesc, idesc, accum);
               accum = 1u;
@@ -666,7 +669,7 @@ struct WPlan {
 WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, bool khs = false, bool kwf = false) {
   WPlan pl;
   if (khs && KH != 3) return pl;
-  if (kwf && (KH != 3 || khs || Cout % 32)) return pl;
+  if (kwf && (KH != 3 || Cout % (khs ? 64 : 32))) return pl;      // kw-fold: Cout blocks of 32 (all kernel rows) or 64 (with kh-split)
   if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
   const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
@@ -681,7 +684,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   const int hwr = khs ? 0 : hw;                           // kh-split: the slab starts at the CTA's kernel row, no row halo
   for (int c = (KS == 1 ? 256 : (khs ? 128 : 48)); c >= 16; c -= 16)   // accumulators (KS*KS, or KS with kh-split) x NB columns must fit 512 TMEM columns
     if (Cout % c == 0) { NB = c; break; }
-  if (kwf) NB = 32;
+  if (kwf) NB = khs ? 64 : 32;
   if (!CU || !NB) return pl;
   const int chunks_u = CU / 8, chunks_v = NB / 8;
   // Search the slab shape (w-block WB x R rows): the full-resolution layers are bound by L2->SMEM traffic, so minimise the halo
@@ -696,7 +699,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
       const int RB = R + 2 * hwr;
       if (((CU / 16) * RB * pw) % 4) continue;   // every plane of the slab is its own TMA destination: keep it 128-byte aligned
       size_t a = (size_t)KD * chunks_u * RB * pw * 16;
-      size_t b = kwf ? (size_t)R * (wb + 2) * 64 : (size_t)chunks_v * R * wb * 16;
+      size_t b = kwf ? (size_t)R * (wb + 2) * NB * 2 : (size_t)chunks_v * R * wb * 16;
       size_t stage = ((a + 1023) & ~(size_t)1023) + ((b + 1023) & ~(size_t)1023);   // both operand tiles start 1024-byte aligned
       // the MMA always reads 16 chunks (128 rows): chunks beyond KD*chunks_u are garbage rows, but must stay inside the allocation
       size_t over = (size_t)(16 - KD * chunks_u > 0 ? 16 - KD * chunks_u : 0) * RB * pw * 16 + (size_t)(2 * pw + 32) * 16;
@@ -714,7 +717,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_cb = Cin / CU; p.n_nb = Cout / NB;
   p.plane_bytes = (uint32_t)chunks_u * p.RB * PW * 16u;
   p.a_bytes = (uint32_t)KD * p.plane_bytes;
-  p.b_bytes = kwf ? (uint32_t)bestR * (WB + 2) * 64u : (uint32_t)chunks_v * bestR * WB * 16u;
+  p.b_bytes = kwf ? (uint32_t)bestR * (WB + 2) * (uint32_t)NB * 2u : (uint32_t)chunks_v * bestR * WB * 16u;
   p.stage_bytes = (uint32_t)((((size_t)p.a_bytes + 1023) & ~(size_t)1023) + (((size_t)p.b_bytes + 1023) & ~(size_t)1023));
   p.kwf = kwf ? 1 : 0;
   { static int b64_env = -1; if (b64_env < 0) { const char* e = getenv("ICH_TC_WGRAD_B64"); b64_env = e ? atoi(e) : 1; }
@@ -775,9 +778,10 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
     // (C, W, H, N*D): the box lands as [row][WB + 2 positions][32 channels] = 64-byte swizzled rows; the column halo is zero-filled
     cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
     cuuint64_t strides[3] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, (cuuint64_t)H * W * dy_ld * 2};
-    cuuint32_t box[4] = {32, (cuuint32_t)(p.WB + 2), (cuuint32_t)p.R, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.NB, (cuuint32_t)(p.WB + 2), (cuuint32_t)p.R, 1};
     CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     p.NB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy, kw-fold) failed with %d", what, (int)r);
   } else {
     const cuuint32_t cbk = 8u * (cuuint32_t)p.bu;     // channels per block = one swizzled row (16 / 32 / 64)
@@ -811,13 +815,18 @@ int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float*
   //              and written back transposed with flipped taps.
   static int mode_env = -1, kwf_env = -1;
   if (mode_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KHS"); mode_env = e ? atoi(e) : 1; }
-  if (kwf_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KWF"); kwf_env = e ? atoi(e) : 1; }
+  if (kwf_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KWF"); kwf_env = e ? atoi(e) : 3; }
   const size_t n_dw = (size_t)Cout * Cin * KD * KH * KW;
   //   kw-fold  : Cout blocks of 32 with the three kw taps folded into N = 96 (an MMA costs 32 + N/4 cycles of operand fetch for
   //              N <= 128, scratch/mma_rate2.cu: 3 MMAs of 56 cycles replace 9 of 40) -- the narrow-Cout (32 / 64) layers.
-  if (kwf_env && KH == 3 && (Cout == 32 || (Cout == 64 && (kwf_env & 2)))) {
+  if (kwf_env && KH == 3 && Cout == 32) {
     WPlan pk = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW, false, true);
     if (pk.ok) return launch_conv_tc_wgrad(pk, x, x_ld, dy, dy_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<kwf>");
+  }
+  //   kw-fold + kh-split : Cout = 64 layers, N = 192 (96 cycles for three taps instead of 3 x 48), one kernel row per CTA
+  if ((kwf_env & 2) && KH == 3 && Cout == 64) {
+    WPlan pk = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW, true, true);
+    if (pk.ok) return launch_conv_tc_wgrad(pk, x, x_ld, dy, dy_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<khs,kwf>");
   }
   if (mode_env && KH == 3) {
     if (Cout % 64 == 0) {
