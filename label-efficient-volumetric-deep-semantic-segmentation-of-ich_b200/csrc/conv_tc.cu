@@ -36,13 +36,17 @@ struct Params {
 
 constexpr int STAGES = 2;        // weight-gradient kernel
 constexpr int MAX_STAGES = 8;    // forward kernel: runtime depth (2 for the big 3x3 slabs, up to 8 for the small 1x1 GEMM stages)
-constexpr int NUM_THREADS = 224;   // slab kernel: warp 0 TMA, warps 1 and 6 MMA issuers (even / odd tiles), warps 2..5 epilogue
+// slab kernel: warp 0 TMA, warps 1 and 2 MMA issuers (even / odd tiles), warp 3 idle, warps 4.. epilogue.  Four epilogue warps when the
+// BatchNorm statistics are fused (128 statistic registers per thread), eight otherwise (two per TMEM lane quadrant, each taking half of
+// the accumulator columns): the transposed-conv scatter epilogue (16 column chunks per tile) was bound by its four warps.
 constexpr int F_ISSUERS = 2;
+template <bool STATS> __host__ __device__ constexpr int f_epi_warps() { return STATS ? 4 : 8; }
+template <bool STATS> __host__ __device__ constexpr int f_threads() { return 32 * (4 + f_epi_warps<STATS>()); }
 constexpr int W_THREADS = 256;   // weight-gradient kernel: warp 0 TMA, warps 1 / 6 / 7 MMA issuers (one per accumulator group), warps 2..5 epilogue
 constexpr int W_ISSUERS = 3;
 
 template <int KS, bool STATS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(f_threads<STATS>(), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage0 A|B][stage1 A|B] ... then barriers
@@ -59,7 +63,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], F_ISSUERS); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], F_ISSUERS); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], F_ISSUERS); mbar_init(&tempty_bar[a], f_epi_warps<STATS>()); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -102,12 +106,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 || warp == 6) {
+  } else if (warp == 1 || warp == 2) {
     // ===================================================== MMA issuers (warp-uniform loops, elected lane issues).  One warp's issue
     // loop costs more cycles per MMA (~68) than an N <= 64 MMA itself (40-48, profiles/r01_mma_rate2.txt): two warps on different SM
     // sub-partitions issue the even and the odd M tiles of every tap.
     {
-      const int ii = warp == 1 ? 0 : 1;
+      const int ii = warp - 1;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
       // The single issuing thread is the critical resource (measured: ~130 cycles per MMA when descriptors were rebuilt
       // from scratch): keep the per-MMA work to two adds + one register pack.  Descriptor = {lo: start>>4 | LBO, hi: const}.
@@ -166,10 +170,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    // ===================================================== epilogue warps (2..5): TMEM lane quadrant = warp % 4
+  } else if (warp >= 4) {
+    // ===================================================== epilogue warps (4..): TMEM lane quadrant = warp % 4; with eight warps the
+    // second set (warps 8..11) takes the upper half of the accumulator columns of every tile
     const int q = warp & 3;
     const int l = q * 32 + lane;
+    const int eset = (warp - 4) >> 2;
+    const int c_lo = (f_epi_warps<STATS>() == 8 && p.NB >= 32) ? eset * (p.NB / 32) * 16 : 0;
+    const int c_hi = (f_epi_warps<STATS>() == 8 && p.NB >= 32) ? (eset == 0 ? (p.NB / 32) * 16 : p.NB) : (eset == 0 ? p.NB : 0);
     uint32_t it = 0;
     float csum[STATS ? 64 : 1], csq[STATS ? 64 : 1];
     if (STATS) {
@@ -197,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
 #pragma unroll
         for (int c0 = 0; c0 < (KS == 1 ? 256 : 64); c0 += 16) {
-          if (c0 < p.NB) {
+          if (c0 >= c_lo && c0 < c_hi) {
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
             tmem_ld_wait();
@@ -240,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (lane == 0) { atomicAdd(&s_stat[0][k], a); atomicAdd(&s_stat[1][k], b); }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp == 2) {
+      if (warp == 4) {
         for (int k = lane; k < p.NB; k += 32) {
           atomicAdd(&p.stat_sum[nb_fixed * p.NB + k], (double)s_stat[0][k]);
           atomicAdd(&p.stat_sumsq[nb_fixed * p.NB + k], (double)s_stat[1][k]);
@@ -410,9 +418,9 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
   grid = grid / p.n_nb * p.n_nb;             // every CTA owns one cout block; n_items is a multiple of n_nb
   if (grid < p.n_nb) grid = p.n_nb;
-  if (p.KS == 3 && stat_sum) conv_tc_kernel<3, true><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else if (p.KS == 3) conv_tc_kernel<3, false><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else conv_tc_kernel<1, false><<<(unsigned)grid, NUM_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  if (p.KS == 3 && stat_sum) conv_tc_kernel<3, true><<<(unsigned)grid, f_threads<true>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else if (p.KS == 3) conv_tc_kernel<3, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else conv_tc_kernel<1, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
   return ich_check_launch(what);
 }
 
