@@ -31,12 +31,12 @@ CONV_FLOP_PER_STEP = 9118.5e9            # SURVEY section 8d, algorithmic 2*M*N*
 
 def ncu_traffic():
     """DRAM bytes of the dominant conv launch (u2.c1 forward, 64->32 @ 8x64x128x128, plane-streaming kernel) from the committed
-    `ncu --set full` extract: dram__bytes_read.sum + dram__bytes_write.sum of the first row of profiles/r01_ncu_u2c1_v5_raw.csv
+    `ncu --set full` extract: dram__bytes_read.sum + dram__bytes_write.sum of the first row of profiles/r01_ncu_u2c1_v6_raw.csv
     (rows: forward, data-gradient, weight-gradient of that layer).  Algorithmic bytes of that launch: input 1.074 GB + output
     0.537 GB (bf16, each touched once)."""
     try:
         import csv
-        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_u2c1_v5_raw.csv'))))
+        rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_u2c1_v6_raw.csv'))))
         hdr, units, first = rows[0], rows[1], rows[2]
         tot = 0.0
         for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
