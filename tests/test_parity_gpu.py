@@ -646,8 +646,11 @@ def test_training_loop_checkpoint_and_frozen_transfer(golden):
 
 
 FULL_SIZE = [  # BASELINE cfg-3 layer shapes (per-GPU batch 8): N, D, H, W, Cin, Cout
-    (8, 64, 128, 128, 32, 32),     # u2.c2: plane-streaming kernel, 268 M output elements
-    (8, 32, 64, 64, 128, 64),      # u1.c1: slab kernel, wgrad in kh-split mode
+    (8, 64, 128, 128, 32, 32),     # u2.c2: plane-streaming kernel, 268 M output elements; wgrad kw-fold (N = 96)
+    (8, 32, 64, 64, 128, 64),      # u1.c1: slab kernel; wgrad kw-fold + kh-split (N = 192, 128-byte dy rows)
+    (8, 64, 128, 128, 1, 16),      # d0.c1: first layer, tcgen05 im2col kernels (forward + weight gradient)
+    (4, 64, 128, 128, 64, 32),     # u2.c1 (half batch): two Cin blocks in the kw-fold wgrad, KC = 4 in the streaming kernel
+    (8, 16, 32, 32, 64, 128),      # d2.c2: wgrad kh-split with N = 128 (128-byte dy rows, two blocks)
 ]
 
 
@@ -665,7 +668,7 @@ def test_full_size_layer_against_torch_fp32_conv(case):
         wt = (torch.randn(cout, cin, 3, 3, 3, device=DEV, generator=g) * 0.05).bfloat16().float()
         with config.override(precision='bf16', tensor_cores=True):
             y = ops.conv_forward(x, wt, None)
-            dx = ops.conv_dgrad(dy, wt)
+            dx = ops.conv_dgrad(dy, wt) if cin > 1 else None      # the first layer's data gradient is never needed (ICH_B200_INPUT_GRAD=0)
             dw = ops.conv_wgrad(x, dy, wt)
         xr = x.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
         wr = wt.clone().requires_grad_(True)
@@ -675,7 +678,8 @@ def test_full_size_layer_against_torch_fp32_conv(case):
         def relg(a, b):
             return ((a.float() - b.float()).norm() / b.float().norm()).item()
         assert relg(y.permute(0, 4, 1, 2, 3), yr.detach()) < 4e-3
-        assert relg(dx.permute(0, 4, 1, 2, 3), xr.grad) < 4e-3
+        if dx is not None:
+            assert relg(dx.permute(0, 4, 1, 2, 3), xr.grad) < 4e-3
         assert relg(dw, wr.grad) < 2e-3
         # size-independent property: the conv is linear -> conv(2x) == 2 conv(x) exactly in bf16 (power-of-two scaling)
         with config.override(precision='bf16', tensor_cores=True):
