@@ -16,6 +16,7 @@ namespace {
 struct C1Params {
   int N, D, H, W, Cout, relu;
   int x_ld, y_ld;
+  int y32;                // forward: output rows are 32-byte aligned (256-bit stores)
   int nseg;               // 128-voxel segments per image row
   long long n_tiles;      // N * D * H * nseg
 };
@@ -260,8 +261,8 @@ conv_cin1_tc_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ wp
             csum[c0 + 2 * k + 1] += hi; csq[c0 + 2 * k + 1] = fmaf(hi, hi, csq[c0 + 2 * k + 1]);
           }
         }
-        if (c0 + 8 <= p.Cout) *reinterpret_cast<uint4*>(yrow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (c0 + 16 <= p.Cout) *reinterpret_cast<uint4*>(yrow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (c0 + 16 <= p.Cout) st_global_32B(yrow + c0, pk, p.y32 != 0);
+        else if (c0 + 8 <= p.Cout) *reinterpret_cast<uint4*>(yrow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
     tile_next(p, te);
@@ -409,7 +410,8 @@ int ich_conv_cin1_tc_fwd(const void* x, int x_ld, const float* wpack, const floa
   ICH_REQUIRE((sum == nullptr) == (sumsq == nullptr), "ich_conv_cin1_tc_fwd: fused statistics need both buffers");
   ICH_REQUIRE(!sum || (!bias && !relu), "ich_conv_cin1_tc_fwd: the fused-statistics form takes no bias / ReLU (BatchNorm follows)");
   cudaStream_t s = (cudaStream_t)stream;
-  const C1Params p = c1_params(N, D, H, W, Cout, x_ld, y_ld, relu);
+  C1Params p = c1_params(N, D, H, W, Cout, x_ld, y_ld, relu);
+  p.y32 = (((uintptr_t)y & 31) == 0 && y_ld % 16 == 0) ? 1 : 0;
   if (sum) {
     cudaMemsetAsync(sum, 0, sizeof(double) * Cout, s);
     cudaMemsetAsync(sumsq, 0, sizeof(double) * Cout, s);

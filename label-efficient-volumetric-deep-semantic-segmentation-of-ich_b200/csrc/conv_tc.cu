@@ -32,6 +32,7 @@ struct Params {
   double* stat_sum;     // optional fused BatchNorm statistics (per output channel sum / sum of squares of the stored bf16 values)
   double* stat_sumsq;
   int dbg;   // ablation switches for profiling only (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue stores
+  int y32;   // output rows are 32-byte aligned: 256-bit stores
 };
 
 constexpr int STAGES = 2;        // weight-gradient kernel
@@ -202,6 +203,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
         bf16* yrow = p.y + vox * p.y_ld + n0;
         int bias0 = n0;
+        // transposed conv: fine-grid index of tap (0,0,0) of this coarse voxel; a tap (i,j,l) adds i*4HW + j*2W + l
+        const long long fine0 = p.up_fd ? ((((long long)n * p.D + d) * p.up_fd) * (2 * p.H) + 2 * (h0 + r)) * (2LL * p.W) + 2 * (w0 + pos) : 0;
+        const int fine_i = 4 * p.H * p.W, fine_j = 2 * p.W;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
 #pragma unroll
         for (int c0 = 0; c0 < (KS == 1 ? 256 : 64); c0 += 16) {
@@ -210,19 +214,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             tmem_ld16(taddr + (uint32_t)c0, v);
             tmem_ld_wait();
             if (p.up_fd) {   // transposed conv k2 s2: this 16-column chunk belongs to one tap (i, j, l) -> scatter to the fine grid
-              const int col = n0 + c0;
-              const int tap = col / p.up_cout;
-              bias0 = col - tap * p.up_cout - c0;
-              const int ti = tap >> 2, tj = (tap >> 1) & 1, tl = tap & 1;
-              const long long fine = ((((long long)n * p.D + d) * p.up_fd + ti) * (2 * p.H) + (2 * (h0 + r) + tj)) * (2 * p.W) + (2 * (w0 + pos) + tl);
-              yrow = p.y + fine * p.y_ld + bias0;
+              const uint32_t col = (uint32_t)(n0 + c0);
+              const uint32_t tap = col / (uint32_t)p.up_cout;
+              bias0 = (int)(col - tap * (uint32_t)p.up_cout) - c0;
+              const int ti = (int)(tap >> 2), tj = (int)(tap >> 1) & 1, tl = (int)tap & 1;
+              yrow = p.y + (fine0 + ti * fine_i + tj * fine_j + tl) * p.y_ld + bias0;
             }
             if (valid && !(p.dbg & 4)) {
               float f32[16];
+              float bv[16];
+              if (p.bias) {       // 16 consecutive, 64-byte aligned bias values
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(p.bias + bias0 + c0 + 4 * k4);
+                  bv[4 * k4] = t4.x; bv[4 * k4 + 1] = t4.y; bv[4 * k4 + 2] = t4.z; bv[4 * k4 + 3] = t4.w;
+                }
+              }
 #pragma unroll
               for (int k = 0; k < 16; ++k) {
                 float a = __uint_as_float(v[k]);
-                if (p.bias) a += p.bias[bias0 + c0 + k];
+                if (p.bias) a += bv[k];
                 if (p.relu) a = fmaxf(a, 0.f);
                 f32[k] = a;
                 if (STATS && c0 < 64) {   // statistics of the value as stored (bf16-rounded)
@@ -231,8 +242,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                   csq[(c0 + k) & 63] = fmaf(rv, rv, csq[(c0 + k) & 63]);
                 }
               }
-              Vec<bf16>::store(yrow + c0, f32);
-              Vec<bf16>::store(yrow + c0 + 8, f32 + 8);
+              uint32_t pk[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) pk[k] = pack_bf16x2_rn(f32[2 * k], f32[2 * k + 1]);
+              st_global_32B(yrow + c0, pk, p.y32 != 0);
             }
           }
         }
@@ -375,6 +388,8 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
               "%s: pointers / pitches must be 16-byte aligned (x_ld %d, y_ld %d)", what, x_ld, y_ld);
   EncodeTiledFn enc = get_encode();
   ICH_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled not available", what);
+  ICH_REQUIRE(((uintptr_t)bias & 15) == 0, "%s: the bias vector must be 16-byte aligned", what);
+  p.y32 = (((uintptr_t)y & 31) == 0 && y_ld % 16 == 0) ? 1 : 0;
   p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
   p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
   { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }

@@ -34,6 +34,7 @@ struct SParams {
   double* stat_sum;
   double* stat_sumsq;
   int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA slab loads, 4 = no epilogue math / stores
+  int y32;   // output rows are 32-byte aligned: 256-bit stores
 };
 
 constexpr int S_THREADS = 384;      // warp 0: TMA, warps 1 and 2: MMA issuers (even / odd tiles), warp 3: idle, warps 4..11: epilogue (two per TMEM lane quadrant)
@@ -272,8 +273,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           csum[i1] += hi; csq[i1] = fmaf(hi, hi, csq[i1]);
         }
       }
-      *reinterpret_cast<uint4*>(yrow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(yrow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      st_global_32B(yrow + c0, pk, p.y32 != 0);
     };
     long long g_base = 0;
     for (long long sp = s_begin; sp < n_spatial; sp += s_step) {
@@ -450,6 +450,7 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   EncodeTiledFn enc = get_encode();
   SParams& p = pl.p;
   p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
+  p.y32 = (((uintptr_t)y & 31) == 0 && y_ld % 16 == 0) ? 1 : 0;
   p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
   { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (stat_sum) {

@@ -121,6 +121,23 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// 32-byte global store (STG.256, sm_100+): one full L2 sector per lane.  `wide` = the destination is 32-byte aligned; otherwise two
+// 16-byte stores.  A voxel's 16 bf16 channels written as two half-sector stores cost the transposed-conv scatter epilogue 2x.
+__device__ __forceinline__ void st_global_32B(void* p, const uint32_t* w, bool wide) {
+  if (wide) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                 "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  } else {
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *(reinterpret_cast<uint4*>(p) + 1) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
