@@ -115,6 +115,13 @@ int ich_bn_act_bwd_drop(const void* dz, int dz_ld, const void* y, int y_ld, cons
                         const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype, long long M, int C,
                         int relu, int training, float drop_p, long long seed, void* stream);
 
+/* SyncBN form of the backward (multi-GPU): phase 1 = reduction pass only (sums zeroed, then filled with this
+ * rank's partial sums), the caller all-reduces `sums` over the ranks, phase 2 = apply pass only with global_count = rows behind the
+ * statistics over all ranks.  dgamma / dbeta stay per-rank quantities (read them from `sums` between the phases; pass NULL here). */
+int ich_bn_act_bwd_sync(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype, long long M, int C,
+                        int relu, int training, float drop_p, long long seed, int phase, long long global_count, void* stream);
+
 /* ---- nn.MaxPool3d/2d(2,2) (models/networks/UNet.py:82,109); grid args = the INPUT grid ------------------------------ */
 int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
 /* dskip (optional): gradient of the SAME tensor arriving through the skip connection (UNet.py:107,119), added in the same pass */

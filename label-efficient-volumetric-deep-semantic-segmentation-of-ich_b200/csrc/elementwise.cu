@@ -325,11 +325,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ scale, const float* __restrict__ shift,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const double* __restrict__ sums, T* __restrict__ dy, int dy_ld, long long M, int C,
-                                                           int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta, const Drop drop) {
+                                                           int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta, const Drop drop,
+                                                           long long count) {
   constexpr int V = VEC ? Vec<T>::N : 1;
   const int groups = C / V;
   const long long total = M * groups;
-  const float invM = training ? (float)(1.0 / (double)M) : 0.f;
+  const float invM = training ? (float)(1.0 / (double)count) : 0.f;   // count = rows behind the statistics (all ranks with SyncBN)
   extern __shared__ float tot[];   // [2][C]: the replicas summed once per block
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) tot[c] = (float)bn_total(sums, c, C);
   __syncthreads();
@@ -500,11 +501,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const double* __restrict__ sums, T* __restrict__ dy, int dy_ld, long long M, int C,
                                                                 int relu, int training, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                const Drop drop) {
+                                                                const Drop drop, long long count) {
   constexpr int V = Vec<T>::N;
   const int groups = C / V, rpb = 256 / groups;
   const int c = (threadIdx.x % groups) * V;
-  const float invM = training ? (float)(1.0 / (double)M) : 0.f;
+  const float invM = training ? (float)(1.0 / (double)count) : 0.f;   // count = rows behind the statistics (all ranks with SyncBN)
   extern __shared__ float tot[];   // [2][C]: the replicas summed once per block
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tot[i] = (float)bn_total(sums, i, C);
   __syncthreads();
@@ -885,21 +886,22 @@ static void affine_act_launch(const void* y, int y_ld, const float* scale, const
 template <typename T, bool DROPV>
 static void bn_act_bwd_launch(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
                               const float* invstd, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta, long long M, int C, int relu,
-                              int training, const Drop drop, cudaStream_t s) {
+                              int training, const Drop drop, cudaStream_t s, int phases, long long count) {
+  // phases: bit 0 = reduction pass, bit 1 = apply pass (SyncBN all-reduces `sums` between the two)
   const int rows_per_block = 2048;
   unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
   size_t shbytes = sizeof(float) * 2 * C;
   bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
   if (vec && rows_fast_ok(C, Vec<T>::N)) {
     const int grid = rows_grid(M, C, Vec<T>::N);
-    bn_bwd_reduce_rows_kernel<T, DROPV><<<grid, 256, 8 * shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
-    bn_bwd_apply_rows_kernel<T, DROPV><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
+    if (phases & 1) bn_bwd_reduce_rows_kernel<T, DROPV><<<grid, 256, 8 * shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
+    if (phases & 2) bn_bwd_apply_rows_kernel<T, DROPV><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop, count);
   } else if (vec) {
-    bn_bwd_reduce_kernel<T, true, DROPV><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
-    bn_bwd_apply_kernel<T, true, DROPV><<<grid_for(M * (C / Vec<T>::N), 256), 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
+    if (phases & 1) bn_bwd_reduce_kernel<T, true, DROPV><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
+    if (phases & 2) bn_bwd_apply_kernel<T, true, DROPV><<<grid_for(M * (C / Vec<T>::N), 256), 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop, count);
   } else {
-    bn_bwd_reduce_kernel<T, false, DROPV><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
-    bn_bwd_apply_kernel<T, false, DROPV><<<grid_for(M * C, 256), 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop);
+    if (phases & 1) bn_bwd_reduce_kernel<T, false, DROPV><<<blocks, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, rows_per_block, drop);
+    if (phases & 2) bn_bwd_apply_kernel<T, false, DROPV><<<grid_for(M * C, 256), 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop, count);
   }
 }
 
@@ -981,12 +983,14 @@ int ich_affine_act_drop(const void* y, int y_ld, const float* scale, const float
 
 static int bn_act_bwd_impl(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
                            const float* invstd, double* sums /*[ICH_BN_SUM_COPIES*2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
-                           long long M, int C, int relu, int training, const Drop drop, cudaStream_t s, const char* what) {
+                           long long M, int C, int relu, int training, const Drop drop, cudaStream_t s, const char* what, int phases = 3,
+                           long long count = 0) {
   if (M * C == 0) return 0;
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * BN_COPIES, s);
+  if (count <= 0) count = M;
+  if (phases & 1) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C * BN_COPIES, s);
   DISPATCH_T(dtype, what, {
-    if (drop.thr) bn_act_bwd_launch<T, true>(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, M, C, relu, training, drop, s);
-    else bn_act_bwd_launch<T, false>(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, M, C, relu, training, drop, s);
+    if (drop.thr) bn_act_bwd_launch<T, true>(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, M, C, relu, training, drop, s, phases, count);
+    else bn_act_bwd_launch<T, false>(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, M, C, relu, training, drop, s, phases, count);
   })
   return ich_check_launch(what);
 }
@@ -1034,6 +1038,15 @@ int ich_upsample2_bwd(const void* dy, int dy_ld, void* dx, int dx_ld, int dtype,
       upsample2_bwd_kernel<T, false><<<grid_for(in_vox * C, 256), 256, 0, s>>>((const T*)dy, dy_ld, (T*)dx, dx_ld, N, ad, ah, aw, C);
   })
   return ich_check_launch("ich_upsample2_bwd");
+}
+
+int ich_bn_act_bwd_sync(const void* dz, int dz_ld, const void* y, int y_ld, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, double* sums /*[ICH_BN_SUM_COPIES*2*C] workspace*/, void* dy, int dy_ld, float* dgamma, float* dbeta, int dtype,
+                        long long M, int C, int relu, int training, float drop_p, long long seed, int phase, long long global_count, void* stream) {
+  ICH_REQUIRE(phase == 1 || phase == 2, "ich_bn_act_bwd_sync: phase must be 1 (reduce) or 2 (apply), got %d", phase);
+  ICH_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, "ich_bn_act_bwd_sync: dropout probability %g outside [0, 1]", (double)drop_p);
+  return bn_act_bwd_impl(dz, dz_ld, y, y_ld, scale, shift, mean, invstd, sums, dy, dy_ld, dgamma, dbeta, dtype, M, C, relu, training,
+                         make_drop(drop_p, (unsigned long long)seed), (cudaStream_t)stream, "ich_bn_act_bwd_sync", phase, global_count);
 }
 
 int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {

@@ -12,6 +12,9 @@ _state = {
     'input_grad': os.environ.get('ICH_B200_INPUT_GRAD', '0') == '1',
     # lay encoder skip tensors out inside the decoder's concat buffer (no copy for torch.cat([res, up], 1))
     'zero_copy_concat': os.environ.get('ICH_B200_ZERO_COPY_CONCAT', '0') == '1',   # measured slower (strided 2C-pitch reads) -> off
+    # SyncBN (optional): BatchNorm batch statistics and the BN-backward sums are all-reduced over the ranks, so
+    # N GPUs x local batch behave exactly like one GPU with the global batch.  Default off = DistributedDataParallel semantics.
+    'sync_bn': os.environ.get('ICH_B200_SYNC_BN', '0') == '1',
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

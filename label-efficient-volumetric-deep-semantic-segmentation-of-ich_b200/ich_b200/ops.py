@@ -126,6 +126,23 @@ def _cin1_tc(x, cin, cout, k):
     return bool(lib().ich_conv_cin1_tc_supported(n, d, h, w, cout, k[0]))
 
 
+# SyncBN plumbing: (world_size, all_reduce_sum(tensor) -> None in place).  None = resolve from torch.distributed at call time.
+# Tests install a fake pair to emulate several ranks on one GPU.
+SYNC_BN_COMM = None
+
+
+def _sync_bn_comm():
+    """(world, allreduce) when SyncBN is on and there is more than one rank, else None."""
+    if not config.get('sync_bn'):
+        return None
+    if SYNC_BN_COMM is not None:
+        return SYNC_BN_COMM if SYNC_BN_COMM[0] > 1 else None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    return dist.get_world_size(), (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+
+
 # bench.py sets PROFILE = [] to collect (kind, flops, start_event, end_event) per conv kernel launch
 PROFILE = None
 
@@ -326,7 +343,13 @@ class ConvBnRelu(Function):
             y = conv_forward(x, weight, None)
             if training:
                 call('ich_colstats', y.data_ptr(), cout, _dt(y), m, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
-        call('ich_bn_finalize', sums[0].data_ptr(), sums[1].data_ptr(), m, cout, _p(gamma), _p(beta), _p(bias), _p(running_mean),
+        comm = _sync_bn_comm() if training else None
+        m_stat = m
+        if comm is not None:
+            # SyncBN: per-channel sum / sum of squares over ALL ranks (equal local batch sizes, as under the DP sampler)
+            comm[1](sums)
+            m_stat = m * comm[0]
+        call('ich_bn_finalize', sums[0].data_ptr(), sums[1].data_ptr(), m_stat, cout, _p(gamma), _p(beta), _p(bias), _p(running_mean),
              _p(running_var), BN_MOMENTUM, BN_EPS, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
              int(training), _stream())
         if concat_c:
@@ -350,6 +373,7 @@ class ConvBnRelu(Function):
                  _stream())
         ctx.save_for_backward(x, weight, y, stats)
         ctx.training, ctx.relu, ctx.drop = training, relu, (drop_p, seed)
+        ctx.sync = comm is not None
         if concat_c:
             ctx.mark_non_differentiable(buf)
             return z, buf
@@ -369,7 +393,18 @@ class ConvBnRelu(Function):
         sums = torch.empty((BN_SUM_COPIES * 2, cout), dtype=torch.float64, device=y.device)
         dgamma = torch.empty(cout, dtype=torch.float32, device=y.device)
         dbeta = torch.empty(cout, dtype=torch.float32, device=y.device)
-        if ctx.drop[0] > 0.0:
+        comm = _sync_bn_comm() if (ctx.training and ctx.sync) else None
+        if comm is not None:
+            # SyncBN backward: reduction pass -> per-rank d(gamma), d(beta) -> all-reduce of the partial sums -> apply pass
+            args = (dzp, dzld, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+                    sums.data_ptr(), dy.data_ptr(), cout, None, None, _dt(y), m, cout, int(ctx.relu), 1, ctx.drop[0], ctx.drop[1])
+            call('ich_bn_act_bwd_sync', *args, 1, m, _stream())
+            local = sums.view(BN_SUM_COPIES, 2, cout).sum(0)
+            dbeta.copy_(local[0])
+            dgamma.copy_(local[1])
+            comm[1](sums)
+            call('ich_bn_act_bwd_sync', *args, 2, m * comm[0], _stream())
+        elif ctx.drop[0] > 0.0:
             call('ich_bn_act_bwd_drop', dzp, dzld, y.data_ptr(), cout, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
                  stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(), _dt(y), m, cout, int(ctx.relu),
                  int(ctx.training), ctx.drop[0], ctx.drop[1], _stream())

@@ -110,6 +110,64 @@ def test_conv_bn_relu_unit(prec, training, chan):
         assert rel(conv_c.bias.grad, conv.bias.grad) < gt
 
 
+def test_sync_bn_two_emulated_ranks():
+    """SyncBN (ICH_B200_SYNC_BN=1): two ranks with half of the batch each must reproduce one rank with the
+    whole batch -- outputs, running statistics, data gradients, and (summed over ranks) the weight / gamma / beta gradients.
+    The ranks are emulated on one GPU with a recording / replaying all-reduce (three deterministic passes per rank: record the
+    forward sums, record the backward sums under the now-global statistics, final pass)."""
+    import copy
+    g = torch.Generator().manual_seed(5)
+    cin, cout, n, d, h, w = 16, 32, 4, 4, 16, 16
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    dz = torch.randn(n, cout, d, h, w, generator=g)
+    conv = torch.nn.Conv3d(cin, cout, 3, padding=1).to(DEV)
+    bn = torch.nn.BatchNorm3d(cout).to(DEV)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+
+    def run(xh, dzh, comm):
+        bn_t = copy.deepcopy(bn)
+        conv.weight.grad = None
+        xc = cl(xh, torch.float32).requires_grad_(True)
+        old = ops.SYNC_BN_COMM
+        ops.SYNC_BN_COMM = comm
+        try:
+            z = ops.ConvBnRelu.apply(xc, conv.weight, conv.bias, bn_t.weight, bn_t.bias, bn_t.running_mean, bn_t.running_var, True, True)
+            z.backward(cl(dzh, torch.float32))
+        finally:
+            ops.SYNC_BN_COMM = old
+        return dict(z=nc(z), dx=nc(xc.grad), dw=conv.weight.grad.clone(), dg=bn_t.weight.grad.clone(), db=bn_t.bias.grad.clone(),
+                    rm=bn_t.running_mean.clone(), rv=bn_t.running_var.clone())
+
+    with config.override(precision='fp32', sync_bn=True):
+        full = run(x, dz, None)
+        halves = [(x[:2], dz[:2]), (x[2:], dz[2:])]
+        rec = [[], []]          # rec[rank][call] = that rank's local tensor at all-reduce call number `call`
+
+        def make_comm(rank, known_calls):
+            state = {'i': 0}
+
+            def ar(t):
+                i = state['i']
+                state['i'] += 1
+                if len(rec[rank]) <= i:
+                    rec[rank].append(t.clone())
+                else:
+                    rec[rank][i] = t.clone()
+                if i < known_calls:
+                    t.add_(rec[1 - rank][i])        # the other rank's contribution recorded in the previous pass
+            return (2, ar)
+        for known in (0, 1, 2):                      # pass 0: record fwd sums; pass 1: fwd exact, record bwd sums; pass 2: exact
+            outs = [run(xh, dzh, make_comm(r, known)) for r, (xh, dzh) in enumerate(halves)]
+    z2 = torch.cat([outs[0]['z'], outs[1]['z']])
+    dx2 = torch.cat([outs[0]['dx'], outs[1]['dx']])
+    assert rel(z2, full['z']) < 1e-5 and rel(dx2, full['dx']) < 1e-4
+    for k in ('dw', 'dg', 'db'):
+        assert rel(outs[0][k] + outs[1][k], full[k]) < 1e-4, k
+    for r in (0, 1):
+        assert rel(outs[r]['rm'], full['rm']) < 1e-5 and rel(outs[r]['rv'], full['rv']) < 1e-5
+
+
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
 @pytest.mark.parametrize('p', [0.5, 0.1])
 def test_fused_dropout_unit(prec, p):
