@@ -85,6 +85,8 @@ class InfoNCELoss(nn.Module):
     def forward(self, z1, z2):
         if z1.shape[0] != self.set_size or z2.shape[0] != self.set_size:
             raise RuntimeError(f'InfoNCELoss: batch ({z1.shape[0]}) must equal set_size ({self.set_size})')
+        # multi-GPU (not in the reference): with ICH_B200_GLOBAL_NCE=1 the comparison set spans the batches of all ranks
+        z1, z2 = ops.gather_rows(z1), ops.gather_rows(z2)
         p = torch.cat((z1, z2), dim=0).unsqueeze(0)          # [1, 2N, E]
         return ops.InfoNCE.apply(p, self.tau)
 

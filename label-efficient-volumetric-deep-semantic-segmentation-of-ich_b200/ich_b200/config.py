@@ -15,6 +15,9 @@ _state = {
     # SyncBN (optional): BatchNorm batch statistics and the BN-backward sums are all-reduced over the ranks, so
     # N GPUs x local batch behave exactly like one GPU with the global batch.  Default off = DistributedDataParallel semantics.
     'sync_bn': os.environ.get('ICH_B200_SYNC_BN', '0') == '1',
+    # global contrastive set: InfoNCELoss compares against the embeddings of ALL ranks (all-gather) instead of the
+    # local batch only.  Default off = the reference's per-process semantics (each rank an independent replica of the loss).
+    'global_nce': os.environ.get('ICH_B200_GLOBAL_NCE', '0') == '1',
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

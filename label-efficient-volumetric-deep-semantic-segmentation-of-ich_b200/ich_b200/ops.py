@@ -779,6 +779,47 @@ class InfoNCE(Function):
         return dP, None
 
 
+# Cross-rank contrastive set: (world, rank, all_gather(t) -> [world * n, E]).  None = resolve from torch.distributed at call time.
+GLOBAL_NCE_COMM = None
+
+
+def _global_nce_comm():
+    if not config.get('global_nce'):
+        return None
+    if GLOBAL_NCE_COMM is not None:
+        return GLOBAL_NCE_COMM if GLOBAL_NCE_COMM[0] > 1 else None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+
+    def gather(t):
+        out = torch.empty((dist.get_world_size() * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+    return dist.get_world_size(), dist.get_rank(), gather
+
+
+class GatherRows(Function):
+    """z [n, E] of this rank -> rows of all ranks [world * n, E] (rank-major), for a loss that every rank evaluates identically on
+    the gathered set.  Backward keeps this rank's rows and multiplies by `world`: the data-parallel gradient all-reduce AVERAGES the
+    parameter gradients over ranks, and only this rank back-propagates through its own rows."""
+
+    @staticmethod
+    def forward(ctx, z, world, rank, gather):
+        ctx.world, ctx.rank, ctx.n = world, rank, z.shape[0]
+        return gather(z.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n] * float(ctx.world), None, None, None
+
+
+def gather_rows(z):
+    """All ranks' rows when the global contrastive set is enabled (ICH_B200_GLOBAL_NCE=1 under torch.distributed), else z itself."""
+    comm = _global_nce_comm()
+    return z if comm is None else GatherRows.apply(z, *comm)
+
+
 class RegionGather(Function):
     """f1, f2 [bs][H][W][C] + corners [bs][A][2] -> P [bs][2A][K*K*C] (models/optim/LossFunctions.py:321-328)."""
 

@@ -70,6 +70,22 @@ def _worker(rank, world, port, out):
         pred_s, mask_s = infer.sliding_window_predict(net, vol, (4, 8, 8), (4, 4, 8), batch=3, distributed=False)
         assert torch.allclose(pred_d, pred_s, atol=1e-6) and torch.equal(mask_d, mask_s)
         assert sorted(sum((dp.shard_indices(7, r, world) for r in range(world)), [])) == list(range(7))
+
+        # cross-rank contrastive set (ICH_B200_GLOBAL_NCE): gather_rows over gloo; the loss is evaluated identically on every rank,
+        # this rank's gradient = world * its rows of d(loss)/d(gathered), so that the data-parallel AVERAGE is the true gradient
+        from ich_b200 import config, ops
+        with config.override(global_nce=True):
+            torch.manual_seed(7)
+            z_all = torch.randn(world * 3, 5)                # same on every rank; rank r owns rows 3r .. 3r+2
+            z = z_all[3 * rank:3 * rank + 3].clone().requires_grad_(True)
+            gathered = ops.gather_rows(z)
+            assert gathered.shape == (world * 3, 5) and torch.equal(gathered.detach(), z_all)
+            wts = torch.arange(world * 3 * 5, dtype=torch.float32).view(world * 3, 5)
+            (gathered * wts).sum().backward()
+            assert torch.allclose(z.grad, world * wts[3 * rank:3 * rank + 3])
+        with config.override(global_nce=False):
+            z = torch.randn(3, 5, requires_grad=True)
+            assert ops.gather_rows(z) is z
         out.put((rank, 'ok'))
     except Exception as e:  # noqa: BLE001
         import traceback

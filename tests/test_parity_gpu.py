@@ -376,6 +376,38 @@ def test_infonce_against_reference_vectors(golden):
         assert rel(f1.grad, c['g1']) < 1e-4 and rel(f2.grad, c['g2']) < 1e-4
 
 
+def test_global_contrastive_set_emulated_ranks():
+    """ICH_B200_GLOBAL_NCE=1: InfoNCE over the embeddings of all ranks.  Two ranks emulated on one GPU (the other
+    rank's rows are constants delivered by a fake all-gather): loss = closed form on the gathered set, local gradient =
+    world * d(loss)/d(local rows) so that the data-parallel gradient AVERAGE is the true gradient."""
+    from src.models.optim import LossFunctions as LF
+    g = torch.Generator().manual_seed(9)
+    n, e, tau, world = 4, 16, 0.2, 2
+    z = [[F.normalize(torch.randn(n, e, generator=g), dim=1) for _ in range(2)] for _ in range(world)]     # z[rank][view]
+    ref_in = [[t.clone().requires_grad_(True) for t in zr] for zr in z]
+    ref = LO.info_nce_loss(torch.cat([ref_in[0][0], ref_in[1][0]]), torch.cat([ref_in[0][1], ref_in[1][1]]), tau)
+    ref.backward()
+    for rank in range(world):
+        calls = {'i': 0}
+
+        def gather(t, rank=rank, calls=calls):
+            view = calls['i'] % 2
+            calls['i'] += 1
+            parts = [t if r == rank else z[r][view].to(DEV) for r in range(world)]
+            return torch.cat(parts)
+        old = ops.GLOBAL_NCE_COMM
+        ops.GLOBAL_NCE_COMM = (world, rank, gather)
+        try:
+            with config.override(global_nce=True):
+                z1, z2 = z[rank][0].to(DEV).requires_grad_(True), z[rank][1].to(DEV).requires_grad_(True)
+                v = LF.InfoNCELoss(set_size=n, tau=tau, device=DEV)(z1, z2)
+                v.backward()
+        finally:
+            ops.GLOBAL_NCE_COMM = old
+        assert abs(v.item() - ref.item()) < 1e-5 * abs(ref.item())
+        assert rel(z1.grad, world * ref_in[rank][0].grad) < 1e-4 and rel(z2.grad, world * ref_in[rank][1].grad) < 1e-4
+
+
 def test_confusion_matrix():
     from src.utils.tensor_utils import batch_binary_confusion_matrix
     g = torch.Generator().manual_seed(8)
