@@ -23,6 +23,7 @@ struct SParams {
   int WB, PW, R, RB, T, row_mode, NB;
   int n_wb, n_rb, n_nb, KC;
   int DS, n_ds;
+  int slots, slot_shift;     // accumulator ring size (4 or 8) and log2 of it
   int stages;
   int b_resident;            // 1: the weights of ALL channel chunks stay in shared memory for the CTA's lifetime (stage = slab only)
   uint32_t a_bytes, a_tx_bytes, b_bytes, stage_bytes, w_offset, tmem_cols;
@@ -41,7 +42,7 @@ constexpr int S_THREADS = 384;      // warp 0: TMA, warps 1 and 2: MMA issuers (
 constexpr int S_EPI_WARPS = 8;
 constexpr int S_ISSUERS = 2;
 constexpr int S_MAX_STAGES = 6;
-constexpr int SLOTS = 4;
+constexpr int MAX_SLOTS = 8;          // accumulator ring: p.slots = 4 or 8 output planes (power of two)
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
   asm volatile(
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(S_THREADS, 1)
 conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const SParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[S_MAX_STAGES], empty_bar[S_MAX_STAGES], tfull_bar[SLOTS], tempty_bar[SLOTS], w_bar;
+  __shared__ __align__(8) uint64_t full_bar[S_MAX_STAGES], empty_bar[S_MAX_STAGES], tfull_bar[MAX_SLOTS], tempty_bar[MAX_SLOTS], w_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stat[2][64];          // per-CTA BatchNorm partial sums (one global atomic per channel per CTA)
 
@@ -81,7 +82,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], S_ISSUERS); }
-    for (int a = 0; a < SLOTS; ++a) { mbar_init(&tfull_bar[a], S_ISSUERS); mbar_init(&tempty_bar[a], S_EPI_WARPS); }
+    for (int a = 0; a < MAX_SLOTS; ++a) { mbar_init(&tfull_bar[a], S_ISSUERS); mbar_init(&tempty_bar[a], S_EPI_WARPS); }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
@@ -92,7 +93,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const uint32_t tmem_base = tmem_base_smem;
   if (warp >= 4 && warp <= 7) {   // all accumulator slots start out zero: every MMA accumulates
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    for (uint32_t c = 0; c < (uint32_t)(p.T * SLOTS * p.NB); c += 16) tmem_st16_zero(lane_base + c);
+    for (uint32_t c = 0; c < (uint32_t)(p.T * p.slots * p.NB); c += 16) tmem_st16_zero(lane_base + c);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -149,7 +150,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
     const uint32_t row16 = ((uint32_t)p.PW * 32u) >> 4;
     const uint32_t tile16 = (p.row_mode ? (uint32_t)p.PW : 128u) * 2u;
-    const uint32_t tstep = (uint32_t)SLOTS * NB;                      // TMEM columns between consecutive tiles
+    const uint32_t tstep = (uint32_t)p.slots * NB;                      // TMEM columns between consecutive tiles
     const int T = p.T;
     int stage = 0; uint32_t phase = 0;
     long long g_base = 0;                                              // output planes completed by this CTA so far
@@ -165,7 +166,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           const int lo = max(d0, pl - 1), hi = min(dend - 1, pl + 1);
           for (int d = acquired + 1; d <= hi; ++d) {                   // first touch of an output plane: its slot must be drained + zeroed
             const long long g = g_base + (d - d0);
-            mbar_wait(&tempty_bar[g & 3], (uint32_t)(((g >> 2) & 1) ^ 1));
+            mbar_wait(&tempty_bar[g & (p.slots - 1)], (uint32_t)(((g >> p.slot_shift) & 1) ^ 1));
             acquired = d;
           }
           tc_fence_after();
@@ -176,8 +177,8 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           bool two_runs;
           {
             const uint32_t g0 = (uint32_t)(g_base + (lo - d0));
-            const int s0 = (int)(g0 & 3u), cnt = hi - lo + 1;
-            const int m0 = min(cnt, SLOTS - s0);
+            const int s0 = (int)(g0 & (uint32_t)(p.slots - 1)), cnt = hi - lo + 1;
+            const int m0 = min(cnt, p.slots - s0);
             r_dcol0 = tmem_base + (uint32_t)s0 * NB + (uint32_t)ii * tstep;
             r_idesc0 = idesc_base | ((((uint32_t)m0 * NB) >> 3) << 17);
             r_brow0 = (uint32_t)(lo - (pl - 1)) * NB * 2u;                 // kd' = d - pl + 1, rows of 32 B = 2 units
@@ -232,7 +233,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int dc = pl - 1;                                          // output plane completed by this step
         if (dc >= d0 && dc < dend) {
           const long long g = g_base + (dc - d0);
-          if (elect_one()) umma_commit(&tfull_bar[g & 3]);
+          if (elect_one()) umma_commit(&tfull_bar[g & (p.slots - 1)]);
           __syncwarp();
         }
       }
@@ -285,8 +286,8 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       const int d0 = ds * p.DS, dend = min(p.D, d0 + p.DS);
       for (int d = d0; d < dend; ++d) {
         const long long g = g_base + (d - d0);
-        const int slot = (int)(g & 3);
-        mbar_wait(&tfull_bar[slot], (uint32_t)((g >> 2) & 1));
+        const int slot = (int)(g & (p.slots - 1));
+        mbar_wait(&tfull_bar[slot], (uint32_t)((g >> p.slot_shift) & 1));
         tc_fence_after();
         for (int tt = eset; tt < p.T; tt += 2) {
           const int f = (p.row_mode ? tt * p.PW : tt * 128) + l;
@@ -294,7 +295,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W) && plain;
           const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
           bf16* yrow = p.y + vox * p.y_ld + n0;
-          const uint32_t taddr = lane_base + (uint32_t)((tt * SLOTS + slot) * p.NB);
+          const uint32_t taddr = lane_base + (uint32_t)((tt * p.slots + slot) * p.NB);
           if ((p.NB & 31) == 0) {
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {       // compile-time column offsets: the statistics stay in registers
@@ -371,6 +372,14 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
     if (Cout % c == 0) { NB = c; break; }
   if (!NB) return pl;
   const bool row_mode = (WB == 128);
+  // Ring of 8 output planes for the narrowest cout block: the three live planes of an input plane wrap around the ring (and the MMA
+  // of N = 3*NB splits into two) for 2 of every `slots` planes -- a quarter instead of half of them.  Measured: a win for NB = 16
+  // (d0.c2 data-gradient 0.328 -> 0.293 ms, the tile count per item stays 4), a loss for NB = 32 (only 2 tiles per item fit the 512
+  // TMEM columns: twice the halo rows and half the MMAs per pipeline stage; u2.c1 forward 0.744 -> 0.849 ms).  ICH_TC_STREAM_SLOTS=32
+  // forces it for NB = 32 (experiments).
+  static int slots_env = -1;
+  if (slots_env < 0) { const char* e = getenv("ICH_TC_STREAM_SLOTS"); slots_env = e ? atoi(e) : 16; }
+  const int SLOTS = (slots_env >= 8 && NB <= slots_env && NB <= 32) ? 8 : 4;
   const int Tmax = 512 / (SLOTS * NB);
   const uint32_t b_bytes = 27u * NB * 32u;
   int bestR = 0, bestT = 0, bestStages = 0, bestRes = 0;
@@ -420,6 +429,7 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
   p.w_offset = (uint32_t)((size_t)bestStages * p.stage_bytes);   // resident weights sit after the slab stages (1024-byte aligned)
   uint32_t cols = 32;
   while (cols < (uint32_t)(SLOTS * bestT * NB)) cols <<= 1;
+  p.slots = SLOTS; p.slot_shift = SLOTS == 8 ? 3 : 2;
   p.tmem_cols = cols;
   p.n_items = (long long)N * p.n_ds * p.n_rb * p.n_wb * p.n_nb;
   pl.smem_bytes = best_smem;
