@@ -606,7 +606,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           // positions (LBO = 64 B), i.e. dy[q + j - 1] for x position q: column block j is kernel column kw = 2 - j.
           // NB = 64: the same with 128-byte SWIZZLE_128B rows (LBO = 128 B), N = 192, one kernel row per CTA (kh-split).
           const uint32_t KU = NB >> 3;                                             // 16-byte units per dy position: 4 (NB = 32) or 8 (NB = 64)
-          const uint32_t kb_hi = KU == 8 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((512u >> 4) | (1u << 14) | (4u << 29));
+          const uint32_t kb_hi = KU == 8 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : KU == 4 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
           uint32_t bk_row = (((st + p.b_off) & 0x3FFFFu) >> 4) | (KU << 16);       // LBO = one position
           const uint32_t BW = KU * (uint32_t)(p.WB + 2);                           // dy row pitch in 16-byte units
           const bool mine = ii < khn;                                              // kh-split: a single accumulator (issuer 0)
@@ -692,7 +692,7 @@ struct WPlan {
 WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, bool khs = false, bool kwf = false) {
   WPlan pl;
   if (khs && KH != 3) return pl;
-  if (kwf && (KH != 3 || Cout % (khs ? 64 : 32))) return pl;      // kw-fold: Cout blocks of 32 (all kernel rows) or 64 (with kh-split)
+  if (kwf && (KH != 3 || Cout % (khs ? 64 : 16))) return pl;      // kw-fold: Cout blocks of 32 / 16 (all kernel rows) or 64 (with kh-split)
   if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
   const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
@@ -707,7 +707,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   const int hwr = khs ? 0 : hw;                           // kh-split: the slab starts at the CTA's kernel row, no row halo
   for (int c = (KS == 1 ? 256 : (khs ? 128 : 48)); c >= 16; c -= 16)   // accumulators (KS*KS, or KS with kh-split) x NB columns must fit 512 TMEM columns
     if (Cout % c == 0) { NB = c; break; }
-  if (kwf) NB = khs ? 64 : 32;
+  if (kwf) NB = khs ? 64 : (Cout % 32 == 0 ? 32 : 16);
   if (!CU || !NB) return pl;
   const int chunks_u = CU / 8, chunks_v = NB / 8;
   // Search the slab shape (w-block WB x R rows): the full-resolution layers are bound by L2->SMEM traffic, so minimise the halo
@@ -748,7 +748,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   { static int a64_env = -1; if (a64_env < 0) { const char* e = getenv("ICH_TC_WGRAD_A64"); a64_env = e ? atoi(e) : 1; }
     p.a64 = (a64_env && CU % 32 == 0) ? 1 : 0; }
   // kw-fold: the 64-byte-swizzled dy tile sits at the (1024-byte aligned) stage base, the x planes follow it
-  p.a_off = kwf ? p.b_bytes : 0u;
+  p.a_off = kwf ? (uint32_t)(((size_t)p.b_bytes + 1023) & ~(size_t)1023) : 0u;
   p.b_off = kwf ? 0u : (uint32_t)(((size_t)p.a_bytes + 1023) & ~(size_t)1023);   // dy tile (32 / 64 / 128-byte swizzled rows) 1024-byte aligned
   uint32_t cols = 32;
   while (cols < (uint32_t)((khs ? KS : KS * KS) * NB)) cols <<= 1;
@@ -803,7 +803,8 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
     cuuint64_t strides[3] = {(cuuint64_t)dy_ld * 2, (cuuint64_t)W * dy_ld * 2, (cuuint64_t)H * W * dy_ld * 2};
     cuuint32_t box[4] = {(cuuint32_t)p.NB, (cuuint32_t)(p.WB + 2), (cuuint32_t)p.R, 1};
     CUresult r = enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     p.NB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     p.NB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : p.NB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy, kw-fold) failed with %d", what, (int)r);
   } else {
@@ -840,6 +841,18 @@ int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float*
   if (mode_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KHS"); mode_env = e ? atoi(e) : 1; }
   if (kwf_env < 0) { const char* e = getenv("ICH_TC_WGRAD_KWF"); kwf_env = e ? atoi(e) : 3; }
   const size_t n_dw = (size_t)Cout * Cin * KD * KH * KW;
+  // narrow-Cin layers (16 -> 32): with rows = (kd, ci) only 48 of the 128 MMA rows are live; the transposed problem has
+  // rows = (kd, co) = 96 live rows and N = Cin = 16 columns per accumulator (cheaper MMAs, same count)
+  static int swap16_env = -1;
+  if (swap16_env < 0) { const char* e = getenv("ICH_TC_WGRAD_SWAP16"); swap16_env = e ? atoi(e) : 3; }
+  if ((swap16_env & 2) && KH == 3 && KD == 3 && Cin == 16 && Cout % 32 == 0) {
+    // transposed problem WITH the kw-fold on the 16-channel operand: rows = (kd, co) (96 live), N = 3 * 16 = 48 (44-cycle MMAs)
+    WPlan ps = make_wplan(N, D, H, W, Cout, Cin, KD, KH, KW, false, (swap16_env & 2) != 0);
+    if (ps.ok) {
+      ps.p.out_mode = 2;
+      return launch_conv_tc_wgrad(ps, dy, dy_ld, x, x_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<swap>");
+    }
+  }
   //   kw-fold  : Cout blocks of 32 with the three kw taps folded into N = 96 (an MMA costs 32 + N/4 cycles of operand fetch for
   //              N <= 128, scratch/mma_rate2.cu: 3 MMAs of 56 cycles replace 9 of 40) -- the narrow-Cout (32 / 64) layers.
   if (kwf_env && KH == 3 && Cout == 32) {
@@ -861,17 +874,6 @@ int ich_conv_tc_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, float*
         pk.p.out_mode = 2;
         return launch_conv_tc_wgrad(pk, dy, dy_ld, x, x_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<khs,swap>");
       }
-    }
-  }
-  // narrow-Cin layers (16 -> 32): with rows = (kd, ci) only 48 of the 128 MMA rows are live; the transposed problem has
-  // rows = (kd, co) = 96 live rows and N = Cin = 16 columns per accumulator (cheaper MMAs, same count)
-  static int swap16_env = -1;
-  if (swap16_env < 0) { const char* e = getenv("ICH_TC_WGRAD_SWAP16"); swap16_env = e ? atoi(e) : 1; }
-  if (swap16_env && KH == 3 && KD == 3 && Cin == 16 && Cout % 32 == 0) {
-    WPlan ps = make_wplan(N, D, H, W, Cout, Cin, KD, KH, KW);
-    if (ps.ok) {
-      ps.p.out_mode = 2;
-      return launch_conv_tc_wgrad(ps, dy, dy_ld, x, x_ld, dw, n_dw, (cudaStream_t)stream, "ich_conv_tc_wgrad<swap>");
     }
   }
   WPlan pl = make_wplan(N, D, H, W, Cin, Cout, KD, KH, KW);
