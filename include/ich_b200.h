@@ -33,6 +33,10 @@ int ich_layout_nl_to_nc(const void* src, int dtype, int src_ld, float* dst, int 
  *      source dim p_k, source dims whose bit is set in flipmask are reversed; dst dtype fp32 or bf16.                                  */
 int ich_permute5(const float* src, void* dst, int dtype, int d0, int d1, int d2, int d3, int d4, int p0, int p1, int p2, int p3, int p4,
                  int flipmask, void* stream);
+/* batched form: n_jobs packs in one launch; src / dst are HOST arrays of device pointers, dtype / flipmask host arrays [n_jobs],
+ * dims / perm host arrays [n_jobs][5] (used to re-derive every stale weight pack of a network after an optimizer step) */
+int ich_permute5_batch(int n_jobs, const void* const* src, void* const* dst, const int* dtype, const int* dims, const int* perm,
+                       const int* flipmask, void* stream);
 
 /* ---- convolution, "same" padding, stride 1: nn.Conv3d/Conv2d k3 p1 (models/networks/UNet.py:153,155,158,160) and the 1x1
  *      heads (:84, :228).  wpack = [taps*Cin][Cout] fp32.  The data-gradient is the same entry point called with the

@@ -843,6 +843,30 @@ __global__ void __launch_bounds__(256) permute5_kernel(const float* __restrict__
   }
 }
 
+// Batched form: every weight pack of a network that went stale with the optimizer step, in ONE launch (blockIdx.y = job).
+constexpr int PERM_BATCH = 48;
+struct Perm5Job { const float* src; void* dst; int dims[5]; int perm[5]; int flip; int bf16; int total; };
+struct Perm5Batch { Perm5Job job[PERM_BATCH]; };
+__global__ void __launch_bounds__(256) permute5_batch_kernel(const __grid_constant__ Perm5Batch b) {
+  const Perm5Job& q = b.job[blockIdx.y];
+  int sstride[5];
+  sstride[4] = 1;
+  for (int i = 3; i >= 0; --i) sstride[i] = sstride[i + 1] * q.dims[i + 1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < q.total; i += gridDim.x * blockDim.x) {
+    int t = i, off = 0;
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+      const int sd = q.perm[k], n = q.dims[sd];
+      int idx = t % n; t /= n;
+      if ((q.flip >> sd) & 1) idx = n - 1 - idx;
+      off += idx * sstride[sd];
+    }
+    const float v = q.src[off];
+    if (q.bf16) reinterpret_cast<bf16*>(q.dst)[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(q.dst)[i] = v;
+  }
+}
+
 // ---- global average pool over the voxels of each sample: x [N][S][C] -> out fp32 [N][C]; and its backward -----------
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ x, int ld, float* __restrict__ out, long long S, int C) {
@@ -1129,6 +1153,39 @@ int ich_permute5(const float* src, void* dst, int dtype, int d0, int d1, int d2,
   if (total == 0) return 0;
   DISPATCH_T(dtype, "ich_permute5", { permute5_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(src, (T*)dst, q, total); })
   return ich_check_launch("ich_permute5");
+}
+
+int ich_permute5_batch(int n_jobs, const void* const* src, void* const* dst, const int* dtype, const int* dims /*[n][5]*/,
+                       const int* perm /*[n][5]*/, const int* flipmask, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(n_jobs >= 0, "ich_permute5_batch: negative job count");
+  for (int j0 = 0; j0 < n_jobs; j0 += PERM_BATCH) {
+    Perm5Batch b;
+    const int nb = n_jobs - j0 < PERM_BATCH ? n_jobs - j0 : PERM_BATCH;
+    int max_total = 0;
+    for (int j = 0; j < nb; ++j) {
+      Perm5Job& q = b.job[j];
+      q.src = (const float*)src[j0 + j]; q.dst = dst[j0 + j]; q.flip = flipmask[j0 + j];
+      ICH_REQUIRE(dtype[j0 + j] == ICH_F32 || dtype[j0 + j] == ICH_BF16, "ich_permute5_batch: bad dtype %d", dtype[j0 + j]);
+      q.bf16 = dtype[j0 + j] == ICH_BF16;
+      long long total = 1;
+      int seen = 0;
+      for (int k = 0; k < 5; ++k) {
+        q.dims[k] = dims[(j0 + j) * 5 + k]; q.perm[k] = perm[(j0 + j) * 5 + k];
+        ICH_REQUIRE(q.perm[k] >= 0 && q.perm[k] < 5, "ich_permute5_batch: bad permutation");
+        seen |= 1 << q.perm[k];
+        total *= q.dims[k];
+      }
+      ICH_REQUIRE(seen == 31 && total < (1ll << 31), "ich_permute5_batch: bad permutation / tensor too large");
+      q.total = (int)total;
+      if (q.total > max_total) max_total = q.total;
+    }
+    if (max_total == 0) continue;
+    int gx = (max_total + 256 * 8 - 1) / (256 * 8);      // ~8 elements per thread for the largest job
+    if (gx > 64) gx = 64;
+    permute5_batch_kernel<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, s>>>(b);
+  }
+  return ich_check_launch("ich_permute5_batch");
 }
 
 int ich_avgpool_fwd(const void* x, int ld, int dtype, float* out, int N, long long S, int C, void* stream) {

@@ -1,6 +1,8 @@
 """torch.autograd.Function wrappers over the C-ABI kernels. They own save-for-backward and workspaces (torch tensors);
 the library never allocates.  Internal activations are channel-last [N, D, H, W, C] tensors (2-D nets: D = 1) in the
 engine dtype (bf16 or fp32, ich_b200.config).  Call sites cite the reference lines they replace."""
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -65,38 +67,98 @@ def _as5d(w):
     return w if w.dim() == 5 else w.unsqueeze(2)
 
 
+# source dims: conv [co, ci, kd, kh, kw]; transposed conv [ci, co, i, j, l].  kind -> (perm, flipped source dims, bf16?, final shape(a, b, taps))
+_PACK_SPEC = {
+    'conv_fwd':        ((2, 3, 4, 1, 0), (),        False, lambda a, b, t: (t * b, a)),     # [taps*Cin][Cout] fp32
+    'conv_dgrad':      ((2, 3, 4, 0, 1), (2, 3, 4), False, lambda a, b, t: (t * a, b)),     # [taps'*Cout][Cin] fp32, taps flipped
+    'conv_fwd_tc':     ((2, 3, 4, 0, 1), (),        True,  lambda a, b, t: (t, a, b)),      # [taps][Cout][Cin] bf16
+    'conv_dgrad_tc':   ((2, 3, 4, 1, 0), (2, 3, 4), True,  lambda a, b, t: (t, b, a)),      # [taps'][Cin][Cout] bf16
+    'conv_fwd_tc_s':   ((3, 4, 2, 0, 1), (2,),      True,  lambda a, b, t: (t, a, b)),      # plane-streaming kernel: [kh][kw][2-kd][Cout][Cin] bf16
+    'conv_dgrad_tc_s': ((3, 4, 2, 1, 0), (3, 4),    True,  lambda a, b, t: (t, b, a)),      # same for the data-gradient conv
+    'convT_fwd_tc':    ((2, 3, 4, 1, 0), (),        True,  lambda a, b, t: (t * b, a)),     # [taps*Cout][Cin] bf16
+    'convT_dgrad_tc':  ((0, 2, 3, 4, 1), (),        True,  lambda a, b, t: (a, t * b)),     # [Cin][taps*Cout] bf16
+    'convT_fwd':       ((0, 2, 3, 4, 1), (),        False, lambda a, b, t: (a, t * b)),     # [Cin][taps*Cout] fp32
+    'convT_dgrad':     ((2, 3, 4, 1, 0), (),        False, lambda a, b, t: (t * b, a)),     # [taps*Cout][Cin] fp32
+}
+
+# every parameter that has weight packs (weak): refresh_packs() re-derives the packs that went stale with an optimizer step in ONE launch
+_PACKED_PARAMS = weakref.WeakSet()
+
+
+def _pack_key(param):
+    return (param._version, param.data_ptr(), param.device)
+
+
 def _pack(param, kind):
-    key = (param._version, param.data_ptr(), param.device)
+    """Kernel-layout copy of a conv / transposed-conv weight (derived cache, never serialised).  The buffers are persistent per
+    (parameter, kind); `fresh` is the set of kinds that match the parameter's current version."""
     cache = getattr(param, '_ich_packs', None)
-    if cache is None or cache[0] != key:
-        cache = (key, {})
+    key = _pack_key(param)
+    if cache is None or cache['key'][1:] != key[1:]:
+        cache = {'key': key, 'bufs': {}, 'fresh': set()}
         param._ich_packs = cache
-    packs = cache[1]
-    if kind not in packs:
-        # source dims: conv [co, ci, kd, kh, kw]; transposed conv [ci, co, i, j, l].  (perm, flipped source dims, bf16?, final shape)
+        _PACKED_PARAMS.add(param)
+    elif cache['key'] != key:                      # the optimizer mutated the parameter in place
+        cache['key'] = key
+        cache['fresh'] = set()
+    if kind not in cache['fresh']:
+        if kind not in _PACK_SPEC:
+            raise KeyError(kind)
+        perm, flips, bf16, shape_of = _PACK_SPEC[kind]
         w = _as5d(param.detach())
         a, b = w.shape[0], w.shape[1]
         taps = w.shape[2] * w.shape[3] * w.shape[4]
-        spec = {
-            'conv_fwd':        ((2, 3, 4, 1, 0), (),        False, (taps * b, a)),      # [taps*Cin][Cout] fp32
-            'conv_dgrad':      ((2, 3, 4, 0, 1), (2, 3, 4), False, (taps * a, b)),      # [taps'*Cout][Cin] fp32, taps flipped
-            'conv_fwd_tc':     ((2, 3, 4, 0, 1), (),        True,  (taps, a, b)),       # [taps][Cout][Cin] bf16
-            'conv_dgrad_tc':   ((2, 3, 4, 1, 0), (2, 3, 4), True,  (taps, b, a)),       # [taps'][Cin][Cout] bf16
-            'conv_fwd_tc_s':   ((3, 4, 2, 0, 1), (2,),      True,  (taps, a, b)),       # plane-streaming kernel: [kh][kw][2-kd][Cout][Cin] bf16
-            'conv_dgrad_tc_s': ((3, 4, 2, 1, 0), (3, 4),    True,  (taps, b, a)),       # same for the data-gradient conv
-            'convT_fwd_tc':    ((2, 3, 4, 1, 0), (),        True,  (taps * b, a)),      # [taps*Cout][Cin] bf16
-            'convT_dgrad_tc':  ((0, 2, 3, 4, 1), (),        True,  (a, taps * b)),      # [Cin][taps*Cout] bf16
-            'convT_fwd':       ((0, 2, 3, 4, 1), (),        False, (a, taps * b)),      # [Cin][taps*Cout] fp32
-            'convT_dgrad':     ((2, 3, 4, 1, 0), (),        False, (taps * b, a)),      # [taps*Cout][Cin] fp32
-        }
-        if kind not in spec:
-            raise KeyError(kind)
-        perm, flips, bf16, shape = spec[kind]
-        src = w.float().contiguous()
-        dst = torch.empty(shape, dtype=torch.bfloat16 if bf16 else torch.float32, device=w.device)
+        src = w if (w.dtype == torch.float32 and w.is_contiguous()) else w.float().contiguous()
+        dst = cache['bufs'].get(kind)
+        if dst is None:
+            dst = torch.empty(shape_of(a, b, taps), dtype=torch.bfloat16 if bf16 else torch.float32, device=w.device)
+            cache['bufs'][kind] = dst
         call('ich_permute5', src.data_ptr(), dst.data_ptr(), 1 if bf16 else 0, *w.shape, *perm, sum(1 << f for f in flips), _stream())
-        packs[kind] = dst
-    return packs[kind]
+        cache['fresh'].add(kind)
+    return cache['bufs'][kind]
+
+
+def refresh_packs():
+    """Called at the start of a forward pass: every pack that was in use before the last optimizer step is re-derived now, all of
+    them in one kernel launch (ich_permute5_batch) instead of one launch per layer and kind spread over forward and backward."""
+    import ctypes
+    jobs = []
+    dev = None
+    for param in list(_PACKED_PARAMS):
+        cache = getattr(param, '_ich_packs', None)
+        if cache is None or not param.is_cuda or param.dtype != torch.float32 or not param.is_contiguous():
+            continue
+        key = _pack_key(param)
+        if cache['key'][1:] != key[1:]:
+            continue                                # storage moved (.to(), load_state_dict on a new tensor): _pack rebuilds lazily
+        if cache['key'] != key:
+            cache['key'] = key
+            cache['fresh'] = set()
+        stale = [k for k in cache['bufs'] if k not in cache['fresh']]
+        if not stale:
+            continue
+        if dev is None:
+            dev = param.device
+        if param.device != dev:
+            continue
+        w = _as5d(param.detach())
+        for kind in stale:
+            perm, flips, bf16, _ = _PACK_SPEC[kind]
+            jobs.append((w.data_ptr(), cache['bufs'][kind].data_ptr(), 1 if bf16 else 0, tuple(w.shape), perm, sum(1 << f for f in flips)))
+            cache['fresh'].add(kind)
+    if not jobs:
+        return 0
+    n = len(jobs)
+    src = (ctypes.c_void_p * n)(*[j[0] for j in jobs])
+    dst = (ctypes.c_void_p * n)(*[j[1] for j in jobs])
+    dt = (ctypes.c_int * n)(*[j[2] for j in jobs])
+    dims = (ctypes.c_int * (5 * n))(*[d for j in jobs for d in j[3]])
+    perm = (ctypes.c_int * (5 * n))(*[q for j in jobs for q in j[4]])
+    flip = (ctypes.c_int * n)(*[j[5] for j in jobs])
+    with torch.cuda.device(dev):
+        call('ich_permute5_batch', n, ctypes.cast(src, ctypes.c_void_p), ctypes.cast(dst, ctypes.c_void_p), ctypes.cast(dt, ctypes.c_void_p),
+             ctypes.cast(dims, ctypes.c_void_p), ctypes.cast(perm, ctypes.c_void_p), ctypes.cast(flip, ctypes.c_void_p), _stream())
+    return n
 
 
 def _ksize(weight):
@@ -259,6 +321,7 @@ class ToChannelsLast(Function):
     @staticmethod
     def forward(ctx, x):
         _require_cuda(x, 'ToChannelsLast')
+        refresh_packs()                     # start of a forward pass: re-derive the weight packs the optimizer step invalidated
         x = x.contiguous().float()
         ctx.was_4d = x.dim() == 4
         if ctx.was_4d:

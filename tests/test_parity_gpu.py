@@ -408,6 +408,32 @@ def test_global_contrastive_set_emulated_ranks():
         assert rel(z1.grad, world * ref_in[rank][0].grad) < 1e-4 and rel(z2.grad, world * ref_in[rank][1].grad) < 1e-4
 
 
+def test_batched_weight_pack_refresh():
+    """Weight packs are derived caches keyed on the parameter version: after an in-place update (an optimizer step) refresh_packs()
+    re-derives every pack that was in use -- all in one launch -- and the result is identical to packing each one from scratch."""
+    torch.manual_seed(3)
+    w3 = torch.nn.Parameter(torch.randn(32, 16, 3, 3, 3, device=DEV))
+    wt = torch.nn.Parameter(torch.randn(64, 32, 2, 2, 2, device=DEV))
+    w2 = torch.nn.Parameter(torch.randn(16, 8, 3, 3, device=DEV))
+    kinds = {w3: ['conv_fwd_tc', 'conv_dgrad_tc', 'conv_fwd_tc_s', 'conv_dgrad_tc_s', 'conv_fwd', 'conv_dgrad'],
+             wt: ['convT_fwd_tc', 'convT_dgrad_tc', 'convT_fwd', 'convT_dgrad'], w2: ['conv_fwd_tc', 'conv_dgrad']}
+    first = {(id(p_), k): ops._pack(p_, k) for p_, ks in kinds.items() for k in ks}
+    ptrs = {key: t.data_ptr() for key, t in first.items()}
+    ops.refresh_packs()                                   # nothing stale
+    with torch.no_grad():
+        for p_ in kinds:
+            p_.mul_(0.5).add_(0.1)                        # in-place update: version bump, same storage
+    n = ops.refresh_packs()
+    assert n >= sum(len(ks) for ks in kinds.values())
+    for p_, ks in kinds.items():
+        fresh_param = torch.nn.Parameter(p_.detach().clone())
+        for k in ks:
+            got = ops._pack(p_, k)
+            assert got.data_ptr() == ptrs[(id(p_), k)]     # persistent buffers
+            assert torch.equal(got, ops._pack(fresh_param, k)), k
+    assert ops.refresh_packs() == 0
+
+
 def test_confusion_matrix():
     from src.utils.tensor_utils import batch_binary_confusion_matrix
     g = torch.Generator().manual_seed(8)
