@@ -33,6 +33,8 @@ struct Params {
   double* stat_sumsq;
   int dbg;   // ablation switches for profiling only (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue stores
   int y32;   // output rows are 32-byte aligned: 256-bit stores
+  int cw;    // channels per K chunk: 16 (32-byte swizzled rows) for the 3x3 kernels; 16 / 32 / 64 (32 / 64 / 128-byte rows) for the 1x1
+             // GEMMs (transposed conv, heads), whose stages are small and whose TMA loads were bound by the number of 32-byte requests
 };
 
 constexpr int STAGES = 2;        // weight-gradient kernel
@@ -98,8 +100,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             if (p.dbg & 2) { mbar_arrive(&full_bar[stage]); }
             else {
               mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
-              tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - KS / 2, h0 - KS / 2, n * p.D + d - planes_lo);
-              tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb * p.NB, 0);
+              tma_load_4d(sa, &map_x, &full_bar[stage], kc * p.cw, w0 - KS / 2, h0 - KS / 2, n * p.D + d - planes_lo);
+              tma_load_3d(sb, &map_w, &full_bar[stage], kc * p.cw, nb * p.NB, 0);
             }
           }
           __syncwarp();
@@ -120,7 +122,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       const uint32_t plane16 = ((uint32_t)p.RB * p.PW * 32u) >> 4;       // plane stride in 16-byte units
       const uint32_t row16 = ((uint32_t)p.PW * 32u) >> 4;                // one slab row
       const uint32_t btap16 = ((uint32_t)p.NB * 32u) >> 4;               // one tap of the weight tile
-      const uint32_t tile16 = (p.row_mode ? (uint32_t)p.PW : 128u) * 2u; // M-tile step
+      const uint32_t tile16 = (p.row_mode ? (uint32_t)p.PW : 128u) * ((uint32_t)p.cw >> 3); // M-tile step (cw * 2 B per position)
+      // 1x1 GEMMs with wide chunks: rows of 64 / 128 bytes (SWIZZLE_64B / 128B), cw / 16 K-steps of 32 bytes inside every row
+      const uint32_t wide_hi = p.cw == 64 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : p.cw == 32 ? ((512u >> 4) | (1u << 14) | (4u << 29)) : desc_hi;
       const uint32_t NB = (uint32_t)p.NB;
       const int T = p.T;
       int stage = 0; uint32_t phase = 0;
@@ -143,6 +147,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           uint32_t b_lo = ((((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)(kd_lo * KS * KS) * btap16;
           uint32_t accum = (kc == 0) ? 0u : 1u;
           uint32_t a_kd = a_lo0;
+          if (KS == 1) {
+            if (!(p.dbg & 1)) {
+              for (uint32_t ks = 0; ks < ((uint32_t)p.cw >> 4); ++ks) {
+                const uint64_t bdesc = pack64(b_lo + 2u * ks, wide_hi);
+                uint32_t a_lo = a_lo0 + 2u * ks + (uint32_t)ii * tile16;
+                uint32_t dcol = d_tmem + (uint32_t)ii * NB;
+#pragma unroll 2
+                for (int tt = ii; tt < T; tt += F_ISSUERS) {
+                  if (elect_one()) umma_bf16(dcol, pack64(a_lo, wide_hi), bdesc, idesc, accum);
+                  a_lo += F_ISSUERS * tile16;
+                  dcol += F_ISSUERS * NB;
+                }
+                accum = 1u;
+              }
+            }
+          } else
           for (int kd = kd_lo; kd <= kd_hi && !(p.dbg & 1); ++kd, a_kd += plane16) {
             uint32_t a_kh = a_kd;
 #pragma unroll
@@ -288,6 +308,10 @@ struct Plan {
 
 Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, int nb_must_divide = 0) {
   Plan pl;
+  static int cw_env = -1;
+  if (cw_env < 0) { const char* e = getenv("ICH_TC_WIDE_K"); cw_env = e ? atoi(e) : 1; }
+  const int cw = (KH == 1 && cw_env) ? (Cin % 64 == 0 ? 64 : Cin % 32 == 0 ? 32 : 16) : 16;   // channels per K chunk
+  const uint32_t rowb = (uint32_t)cw * 2u;                                                   // bytes per position in a stage
   if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
   const int KS = KH, hw = KS / 2;
   if (Cin % 16 || Cout % 16 || Cin <= 0 || Cout <= 0) return pl;
@@ -307,7 +331,7 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   // amortises the per-MMA operand fetch (~76 cycles per MMA measured for any N <= 64, scratch/mma_rate.cu)
   for (int NB = (KS == 1 ? 256 : 64); NB >= 16; NB -= 16) {
     if (Cout % NB || (nb_must_divide && nb_must_divide % NB)) continue;
-    const uint32_t b_bytes = (uint32_t)taps * 2u * NB * 16u;
+    const uint32_t b_bytes = (uint32_t)taps * NB * rowb;
     for (int R = 1; R <= H && R <= 64; ++R) {
       const int RB = R + 2 * hw;
       const int T = row_mode ? R : (((R - 1) * PW + WB) + 127) / 128;
@@ -315,9 +339,9 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
       if (2 * T * NB <= 512) nacc = 2;
       else if (T * NB <= 512) nacc = 1;
       else continue;
-      uint32_t a_bytes = (uint32_t)KD * 2u * RB * PW * 16u;
-      a_bytes = (a_bytes + 127u) & ~127u;
-      long long over = row_mode ? 0 : ((long long)(128 * T + 2 * hw * PW + 2 * hw) - (long long)RB * PW) * 32;
+      uint32_t a_bytes = (uint32_t)KD * RB * PW * rowb;
+      a_bytes = cw > 16 ? ((a_bytes + 1023u) & ~1023u) : ((a_bytes + 127u) & ~127u);     // the weight tile follows: keep wide-swizzle tiles 1024-aligned
+      long long over = row_mode ? 0 : ((long long)(128 * T + 2 * hw * PW + 2 * hw) - (long long)RB * PW) * (long long)rowb;
       if (over < 0) over = 0;
       size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
       int stages = (int)((SMEM_LIMIT - (size_t)over - 1024) / stage);
@@ -337,16 +361,16 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
     if (KS == 3 && best_cost >= 0) break;    // 3x3: take the largest feasible cout block (fewest slab re-reads)
   }
   const int NB = bestNB;
-  const uint32_t b_bytes = (uint32_t)taps * 2u * NB * 16u;
+  const uint32_t b_bytes = (uint32_t)taps * NB * rowb;
   if (best_cost < 0) return pl;
   Params& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
   p.up_fd = 0; p.up_cout = 0;
   p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hw; p.T = bestT; p.row_mode = row_mode; p.NB = NB;
-  p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / 16; p.taps = taps;
+  p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / cw; p.taps = taps; p.cw = cw;
   p.nacc = bestAcc; p.stages = bestStages;
   p.a_bytes = best_a;
-  p.a_tx_bytes = (uint32_t)KD * 2u * p.RB * PW * 16u;
+  p.a_tx_bytes = (uint32_t)KD * p.RB * PW * rowb;
   p.b_bytes = b_bytes;
   p.stage_bytes = (uint32_t)(((size_t)best_a + b_bytes + 1023) & ~(size_t)1023);
   uint32_t cols = 32;
@@ -404,21 +428,23 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
     // x as (C, W, H, N*D): the box lands as [plane][row][pos][16 ch] = 32-byte rows, 32B-swizzled (full 32 B L2 sectors)
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
     cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2};
-    cuuint32_t box[4] = {16, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)KD};
+    cuuint32_t box[4] = {(cuuint32_t)p.cw, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)KD};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     p.cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : p.cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(x) failed with %d", what, (int)r);
   }
   {
     // w [taps][Cout][Cin] as (Cin, Cout, taps): box = [tap][NB rows][16 ch], same 32-byte swizzled rows
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)p.taps};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-    cuuint32_t box[3] = {16, (cuuint32_t)p.NB, (cuuint32_t)p.taps};
+    cuuint32_t box[3] = {(cuuint32_t)p.cw, (cuuint32_t)p.NB, (cuuint32_t)p.taps};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : p.cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(w) failed with %d", what, (int)r);
   }
   static bool attr_set = false;
