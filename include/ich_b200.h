@@ -128,6 +128,10 @@ int ich_bn_act_bwd_sync(const void* dz, int dz_ld, const void* y, int y_ld, cons
 
 /* ---- nn.MaxPool3d/2d(2,2) (models/networks/UNet.py:82,109); grid args = the INPUT grid ------------------------------ */
 int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream);
+/* same, also copying x into `skip` (a channel slab of the decoder's concat buffer, pitch skip_ld): the encoder block output is both
+ * pooled and kept as the skip tensor (UNet.py:107-109,119), so the concat costs no pass of its own */
+int ich_maxpool2_fwd_skip(const void* x, int x_ld, void* y, int y_ld, void* skip, int skip_ld, int dtype, int N, int D, int H, int W, int C,
+                          int FD, void* stream);
 /* dskip (optional): gradient of the SAME tensor arriving through the skip connection (UNet.py:107,119), added in the same pass */
 int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W, int C,
                      int FD, const void* dskip, int dskip_ld, void* stream);

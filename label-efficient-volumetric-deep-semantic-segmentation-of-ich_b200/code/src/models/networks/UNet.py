@@ -168,15 +168,16 @@ class _UNetBase(nn.Module):
         n_down = len(self.down_block)
         ups = list(getattr(self, 'up_samp', []))
         for i, block in enumerate(self.down_block):         # UNet.py:106-109
-            # skip tensor i is consumed by decoder stage (n_down - 1 - i): lay it out inside that stage's concat buffer
+            # skip tensor i is consumed by decoder stage (n_down - 1 - i): the pool kernel lays it out inside that stage's concat
+            # buffer on the way (no copy pass for torch.cat([res, up], 1), UNet.py:119)
             j = n_down - 1 - i
             concat_c = ups[j].out_channels if (_cfg.get('zero_copy_concat') and j < len(ups)
                                                and isinstance(ups[j], (nn.ConvTranspose3d, nn.ConvTranspose2d))) else 0
-            x = block.forward_cl(x, concat_c)
-            buf = getattr(x, '_ich_concat_buf', None)
-            skip, x = ops.PoolSkip.apply(x, self._fd)       # skip tensor + pooled tensor; their gradients meet in one kernel
-            if buf is not None:
-                skip._ich_concat_buf = buf
+            x = block.forward_cl(x)
+            out = ops.PoolSkip.apply(x, self._fd, concat_c)  # skip tensor + pooled tensor; their gradients meet in one kernel
+            skip, x = out[0], out[1]
+            if concat_c:
+                skip._ich_concat_buf = out[2]
             res.append(skip)
         return self.bottleneck_block.forward_cl(x), res     # UNet.py:112
 

@@ -574,7 +574,7 @@ inline int rows_grid(long long M, int C, int V) {
 // Tie rule = ATen max_pool3d_with_indices: scan (d,h,w) in order, update on strict '>' (NaN propagates) -> first max wins.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld, int N, int D,
-                                                          int H, int W, int C, int FD) {
+                                                          int H, int W, int C, int FD, T* __restrict__ skip, int skip_ld) {
   constexpr int V = VEC ? Vec<T>::N : 1;
   const int groups = C / V, Do = D / FD, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Do * Ho * Wo * groups;
@@ -593,6 +593,10 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T* __restrict__ 
           long long row = (((long long)n * D + dd * FD + a) * H + 2 * ho + b) * W + 2 * wo + e;
           float v[V];
           if (VEC) Vec<T>::load(x + row * x_ld + c, v); else v[0] = to_f32(x[row * x_ld + c]);
+          if (skip) {   // the same tensor is the skip connection: lay it out as a channel slab of the decoder's concat buffer on the way
+            if (VEC) *reinterpret_cast<uint4*>(skip + row * skip_ld + c) = *reinterpret_cast<const uint4*>(x + row * x_ld + c);
+            else skip[row * skip_ld + c] = x[row * x_ld + c];
+          }
 #pragma unroll
           for (int k = 0; k < V; ++k) if (v[k] > best[k] || v[k] != v[k]) best[k] = v[k];
         }
@@ -1073,18 +1077,28 @@ int ich_bn_act_bwd_sync(const void* dz, int dz_ld, const void* y, int y_ld, cons
                          make_drop(drop_p, (unsigned long long)seed), (cudaStream_t)stream, "ich_bn_act_bwd_sync", phase, global_count);
 }
 
-int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  ICH_REQUIRE((FD == 1 || FD == 2) && D % FD == 0 && H % 2 == 0 && W % 2 == 0, "ich_maxpool2_fwd: grid %dx%dx%d not divisible by the pool", D, H, W);
+static int maxpool2_fwd_impl(const void* x, int x_ld, void* y, int y_ld, void* skip, int skip_ld, int dtype, int N, int D, int H, int W, int C,
+                             int FD, cudaStream_t s, const char* what) {
+  ICH_REQUIRE((FD == 1 || FD == 2) && D % FD == 0 && H % 2 == 0 && W % 2 == 0, "%s: grid %dx%dx%d not divisible by the pool", what, D, H, W);
   long long outv = (long long)N * (D / FD) * (H / 2) * (W / 2);
   if (outv * C == 0) return 0;
-  DISPATCH_T(dtype, "ich_maxpool2_fwd", {
-    if (vec_ok<T>(x, x_ld, C) && vec_ok<T>(y, y_ld, C))
-      maxpool_fwd_kernel<T, true><<<grid_for(outv * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, D, H, W, C, FD);
+  DISPATCH_T(dtype, what, {
+    if (vec_ok<T>(x, x_ld, C) && vec_ok<T>(y, y_ld, C) && (!skip || vec_ok<T>(skip, skip_ld, C)))
+      maxpool_fwd_kernel<T, true><<<grid_for(outv * (C / Vec<T>::N), 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, D, H, W, C, FD, (T*)skip, skip_ld);
     else
-      maxpool_fwd_kernel<T, false><<<grid_for(outv * C, 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, D, H, W, C, FD);
+      maxpool_fwd_kernel<T, false><<<grid_for(outv * C, 256), 256, 0, s>>>((const T*)x, x_ld, (T*)y, y_ld, N, D, H, W, C, FD, (T*)skip, skip_ld);
   })
-  return ich_check_launch("ich_maxpool2_fwd");
+  return ich_check_launch(what);
+}
+
+int ich_maxpool2_fwd(const void* x, int x_ld, void* y, int y_ld, int dtype, int N, int D, int H, int W, int C, int FD, void* stream) {
+  return maxpool2_fwd_impl(x, x_ld, y, y_ld, nullptr, 0, dtype, N, D, H, W, C, FD, (cudaStream_t)stream, "ich_maxpool2_fwd");
+}
+
+int ich_maxpool2_fwd_skip(const void* x, int x_ld, void* y, int y_ld, void* skip, int skip_ld, int dtype, int N, int D, int H, int W, int C,
+                          int FD, void* stream) {
+  ICH_REQUIRE(skip != nullptr, "ich_maxpool2_fwd_skip: the skip destination is required");
+  return maxpool2_fwd_impl(x, x_ld, y, y_ld, skip, skip_ld, dtype, N, D, H, W, C, FD, (cudaStream_t)stream, "ich_maxpool2_fwd_skip");
 }
 
 int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W,

@@ -10,8 +10,9 @@ _state = {
     # compute d(loss)/d(input) when the caller set input.requires_grad_ (models/optim/UNet2D.py:137). The reference
     # trainers never read it; default off saves the first layer's data-gradient.
     'input_grad': os.environ.get('ICH_B200_INPUT_GRAD', '0') == '1',
-    # lay encoder skip tensors out inside the decoder's concat buffer (no copy for torch.cat([res, up], 1))
-    'zero_copy_concat': os.environ.get('ICH_B200_ZERO_COPY_CONCAT', '0') == '1',   # measured slower (strided 2C-pitch reads) -> off
+    # 1 = the max-pool kernel also lays the encoder skip tensor out inside the decoder's concat buffer (no copy pass for
+    # torch.cat([res, up], 1)); measured 0.15-0.2 ms/step SLOWER at cfg-3 than the separate slab copy in the decoder -> off
+    'zero_copy_concat': os.environ.get('ICH_B200_ZERO_COPY_CONCAT', '0') == '1',
     # SyncBN (optional): BatchNorm batch statistics and the BN-backward sums are all-reduced over the ranks, so
     # N GPUs x local batch behave exactly like one GPU with the global batch.  Default off = DistributedDataParallel semantics.
     'sync_bn': os.environ.get('ICH_B200_SYNC_BN', '0') == '1',

@@ -549,25 +549,34 @@ class MaxPool2(Function):
 class PoolSkip(Function):
     """Encoder step of UNet.forward (UNet.py:107-109): the block output is kept as the skip tensor AND max-pooled. One Function
     with two outputs, so that the two gradients of the same tensor (through the decoder concat and through the pooled path)
-    are combined inside the max-pool backward kernel instead of a separate autograd add."""
+    are combined inside the max-pool backward kernel instead of a separate autograd add.
+    concat_c > 0: the pool kernel also writes the tensor into the first channel slab of a [.., C + concat_c] buffer -- the decoder's
+    torch.cat([res, up], 1) buffer (UNet.py:119), which UpConvCat then completes in place (no separate copy pass)."""
 
     @staticmethod
-    def forward(ctx, x, fd):
+    def forward(ctx, x, fd, concat_c=0):
         n, d, h, w, c = x.shape
         y = torch.empty((n, d // fd, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
         xp, xld = _rows(x)
-        call('ich_maxpool2_fwd', xp, xld, y.data_ptr(), c, _dt(x), n, d, h, w, c, fd, _stream())
         ctx.save_for_backward(x)
         ctx.fd = fd
+        if concat_c:
+            ctot = c + concat_c
+            buf = torch.empty((n, d, h, w, ctot), dtype=x.dtype, device=x.device)
+            call('ich_maxpool2_fwd_skip', xp, xld, y.data_ptr(), c, buf.data_ptr(), ctot, _dt(x), n, d, h, w, c, fd, _stream())
+            skip = _alias(buf, (n, d, h, w, c), (d * h * w * ctot, h * w * ctot, w * ctot, ctot, 1))
+            ctx.mark_non_differentiable(buf)
+            return skip, y, buf
+        call('ich_maxpool2_fwd', xp, xld, y.data_ptr(), c, _dt(x), n, d, h, w, c, fd, _stream())
         skip = _alias(x, tuple(x.shape), x.stride())     # same storage, fresh tensor object
         return skip, y
 
     @staticmethod
-    def backward(ctx, dskip, dy):
+    def backward(ctx, dskip, dy, *unused):
         (x,) = ctx.saved_tensors
         n, d, h, w, c = x.shape
         if dy is None:
-            return (dskip.contiguous() if dskip is not None else None), None
+            return (dskip.contiguous() if dskip is not None else None), None, None
         dy = dy.contiguous()
         dx = torch.empty((n, d, h, w, c), dtype=x.dtype, device=x.device)
         xp, xld = _rows(x)
@@ -579,7 +588,7 @@ class PoolSkip(Function):
                 dskip = dskip.contiguous()
                 sp, sld = dskip.data_ptr(), c
         call('ich_maxpool2_bwd', xp, xld, dy.data_ptr(), c, dx.data_ptr(), c, _dt(x), n, d, h, w, c, ctx.fd, sp, sld, _stream())
-        return dx, None
+        return dx, None, None
 
 
 # ---------------------------------------------------------------------------------------------------------------
