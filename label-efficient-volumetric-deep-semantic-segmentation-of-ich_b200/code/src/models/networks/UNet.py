@@ -39,6 +39,16 @@ def _filters(in_channels, top_filter, depth):
     return down, bottleneck
 
 
+# BatchNorm's num_batches_tracked counters of one forward pass are bumped together (one multi-tensor launch instead of one per layer)
+_PENDING_NBT = []
+
+
+def _flush_nbt():
+    if _PENDING_NBT:
+        torch._foreach_add_(_PENDING_NBT, 1)
+        _PENDING_NBT.clear()
+
+
 def _not_built(what):
     raise NotImplementedError(f'ich_b200: {what} is not part of the B200 hot path yet (SURVEY section 8f); '
                               f'refusing to fall back silently')
@@ -70,7 +80,7 @@ class ConvBlock(nn.Module):
             z, buf = z
             z._ich_concat_buf = buf          # the decoder's UpConvCat completes this buffer in place (zero-copy skip concat)
         if training and bn.track_running_stats:
-            bn.num_batches_tracked += 1
+            _PENDING_NBT.append(bn.num_batches_tracked)      # flushed at the end of the enclosing forward (_flush_nbt)
         return z
 
     def forward_cl(self, x, concat_c=0):
@@ -84,7 +94,9 @@ class ConvBlock(nn.Module):
 
     def forward(self, input):
         was_4d = input.dim() == 4
-        return ops.from_channels_last(self.forward_cl(ops.to_channels_last(input)), was_4d)
+        out = ops.from_channels_last(self.forward_cl(ops.to_channels_last(input)), was_4d)
+        _flush_nbt()
+        return out
 
 
 class MLPHead(nn.Module):
@@ -216,6 +228,7 @@ class UNet(_UNetBase):
         x = self._decode(x, res)
         act = 0 if isinstance(self.final_activation, nn.Identity) else (2 if isinstance(self.final_activation, nn.Softmax) else 1)
         out = ops.Head.apply(x, self.final_conv.weight, self.final_conv.bias, act)           # UNet.py:122
+        _flush_nbt()
         if was_4d:
             out = out.squeeze(2)
         if self.return_bottleneck:
@@ -238,6 +251,7 @@ class UNet_Encoder(_UNetBase):
     def forward(self, input):
         was_4d = input.dim() == 4
         x, _ = self._encode(ops.to_channels_last(input))
+        _flush_nbt()
         pooled = ops.GlobalAvgPool.apply(x)                                     # UNet.py:318, fp32 [N, C]
         out = self.mlp_head(pooled)                                             # UNet.py:321
         if self.return_bottleneck:
@@ -266,6 +280,7 @@ class Partial_UNet(_UNetBase):
         x_bottleneck = x
         x = self._decode(x, res[::-1][:self.n_decoder][::-1])                  # UNet.py:425-427
         out = ops.from_channels_last(self.final_conv.forward_cl(x), was_4d)     # UNet.py:430
+        _flush_nbt()
         if self.return_bottleneck:
             return out, ops.from_channels_last(x_bottleneck, was_4d)
         return out
