@@ -644,7 +644,12 @@ TC_CASES = [  # N, D, H, W, Cin, Cout, k3d  -- shapes the tcgen05 kernel must ta
     (1, 20, 8, 32, 32, 128, True),      # plane-streaming kernel: 2 depth segments (16 + 4 planes), 2 cout blocks
     (2, 18, 4, 128, 16, 16, True),      # plane-streaming kernel, row mode, NB = 16, ring wraps many times
     (2, 1, 32, 64, 32, 64, False),      # 2-D, wgrad in kh-split mode (Cout multiple of 64)
-    (1, 4, 16, 128, 64, 32, True),      # wgrad with swapped operands (wide Cin, narrow Cout), w-blocked slab
+    (1, 4, 16, 128, 64, 32, True),      # wgrad kw-fold (N = 96) with two Cin blocks, w-blocked slab
+    (1, 4, 16, 64, 32, 64, True),       # streaming kernel on 64-wide rows (narrow Cin, wide Cout); wgrad kw-fold + kh-split (N = 192)
+    (1, 3, 8, 32, 16, 32, True),        # wgrad: transposed problem with the kw-fold on the 16-channel operand (N = 48)
+    (2, 1, 32, 128, 32, 32, False),     # 2-D wgrad kw-fold (KD = 1)
+    (1, 2, 6, 48, 64, 64, True),        # kw-fold + kh-split on 48-wide rows (one w-block of 48, column halo inside the TMA box)
+    (1, 1, 24, 64, 16, 32, False),      # 2-D, Cin = 16: kw-fold with 16-channel x blocks (32-byte rows)
 ]
 
 
