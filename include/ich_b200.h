@@ -159,6 +159,12 @@ int ich_seg_loss_fwd(const float* pred, const float* mask, int B, long long S, f
 int ich_seg_loss_bwd(const float* pred, const float* mask, const double* acc, const float* gscale, int B, long long S, float P, float eps,
                      float alpha_empty, float w_bce, float w_dice, float beta, float* dpred, void* stream);
 
+/* ---- TverskyLoss (models/optim/LossFunctions.py:65-114): acc as above (P = 1), TL = 1 - (TP+eps)/(TP + beta FN + gamma FP + eps) -------- */
+int ich_tversky_loss_fwd(const float* pred, const float* mask, int B, long long S, float eps, float alpha_empty, float beta, float gamma,
+                         int reduction, double* acc, float* per_sample, float* loss, void* stream);
+int ich_tversky_loss_bwd(const float* mask, const double* acc, const float* gscale, int B, long long S, float eps, float alpha_empty, float beta,
+                         float gamma, float* dpred, void* stream);
+
 /* ---- InfoNCELoss / LocalInfoNCELoss (models/optim/LossFunctions.py:208-230,308-341) ----------------------------------- */
 int ich_infonce_fwd(const float* P, int B, int R, int E, float tau, float* Pn, float* invn, float* lse, float* rowloss, float* loss,
                     unsigned int* counter, void* stream);

@@ -1,10 +1,10 @@
 """B200-native drop-in for the reference's `src.models.optim.LossFunctions` module.
 
-Hot-path losses (BinaryDiceLoss, ComboLoss, InfoNCELoss, LocalInfoNCELoss) keep the reference's constructor
-signatures, assertions and call protocol (/root/reference/code/src/models/optim/LossFunctions.py:14-63, :116-166,
-:168-230, :232-341) but run as fused one-pass CUDA kernels (ich_b200.ops).  The side-track losses the module must still
-export (TverskyLoss :65-114, DiscountedL1 :343-409, GDL :411-448, HSCLoss :450-470) are plain
-torch restatements -- they are not on the hot path.
+Hot-path losses (BinaryDiceLoss, ComboLoss, InfoNCELoss, LocalInfoNCELoss) and TverskyLoss keep the
+reference's constructor signatures, assertions and call protocol (/root/reference/code/src/models/optim/LossFunctions.py:14-63,
+:65-114, :116-166, :168-230, :232-341) but run as fused one-pass CUDA kernels (ich_b200.ops).  The side-track losses the
+module must still export (DiscountedL1 :343-409, GDL :411-448, HSCLoss :450-470) are plain torch
+restatements -- they are not on the hot path.
 """
 import os
 import sys
@@ -133,27 +133,28 @@ class LocalInfoNCELoss(nn.Module):
         return ops.InfoNCE.apply(p, self.tau)
 
 
-# ---------------------------------------------------------------------------------------------------------------------
-# Out-of-scope losses (plain torch; exported because other reference trainers import them by name)
-# ---------------------------------------------------------------------------------------------------------------------
 class TverskyLoss(nn.Module):
-    """1 - (TP + 1) / (TP + beta*FN + gamma*FP + 1), alpha-scaled on empty masks."""
+    """1 - (TP + 1) / (TP + beta*FN + gamma*FP + 1) per sample, scaled by alpha when the mask is empty (reference :65-114).
+    Runs on the engine: the Dice reduction pass + a finalize, and a backward pass that reads only the mask."""
 
     def __init__(self, alpha=1.0, beta=0.5, gamma=0.5, reduction='mean'):
         super(TverskyLoss, self).__init__()
-        self.alpha, self.beta, self.gamma, self.reduction, self.eps = alpha, beta, gamma, reduction, 1
+        self.alpha = alpha
+        self.beta = beta
+        self.gamma = gamma
+        self.reduction = reduction
+        self.eps = 1
 
     def forward(self, pred, mask):
         assert pred.shape == mask.shape, f'Prediction and Mask should have the same dimensions! Given: Prediction {pred.shape} / Mask {mask.shape}'
-        dims = tuple(range(1, pred.ndim))
-        tp = (pred * mask).sum(dims)
-        fp = (pred * (1 - mask)).sum(dims)
-        fn = ((1 - pred) * mask).sum(dims)
-        tl = 1 - (tp + self.eps) / (tp + self.beta * fn + self.gamma * fp + self.eps)
-        tl = torch.where(mask.sum(dims) > 0, tl, self.alpha * tl)
-        return _apply_reduction(tl, self.reduction)
+        red = self.reduction if self.reduction in ('mean', 'sum', 'none') else 'none'
+        out = ops.TverskyLossFn.apply(pred, mask, self.eps, self.alpha, self.beta, self.gamma, red)
+        return out if self.reduction in ('mean', 'sum', 'none') else None   # the reference returns None for unknown reductions
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Out-of-scope losses (plain torch; exported because other reference trainers import them by name)
+# ---------------------------------------------------------------------------------------------------------------------
 class DiscountedL1(nn.Module):
     """L1 on the mask, discounted by gamma ** (distance to the nearest non-mask border pixel)."""
 

@@ -252,6 +252,42 @@ __global__ void __launch_bounds__(256) seg_loss_bwd_kernel(const float* __restri
   }
 }
 
+// ---- Tversky loss (models/optim/LossFunctions.py:65-114) ------------------------------------------------------------------
+// Uses seg_loss_reduce_kernel with P = 1: acc[b] = { TP = sum p*m, sum p, sum m, sum m, - }  ->  FP = sum p - TP, FN = sum m - TP.
+// TL = 1 - (TP + eps) / (TP + beta*FN + gamma*FP + eps), times alpha_empty when the mask has no positive voxel.
+__global__ void tversky_finalize_kernel(const double* __restrict__ acc, int B, float eps, float alpha_empty, float beta, float gamma, int reduction,
+                                        float* __restrict__ per_sample, float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float local = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double tp = acc[b * 5 + 0], fp = acc[b * 5 + 1] - tp, fn = acc[b * 5 + 2] - tp;
+    float tl = 1.f - (float)((tp + eps) / (tp + (double)beta * fn + (double)gamma * fp + eps));
+    if (!(acc[b * 5 + 3] > 0.0)) tl *= alpha_empty;
+    per_sample[b] = tl;
+    local += tl;
+  }
+  float v1[1] = {local};
+  block_sum<1>(v1, sh);
+  if (threadIdx.x == 0) loss[0] = reduction == 1 ? v1[0] / (float)B : v1[0];
+}
+
+// dTL/dp = -( m*den - num*(m - beta*m + gamma*(1 - m)) ) / den^2   (dTP/dp = m, dFN/dp = -m, dFP/dp = 1 - m)
+__global__ void __launch_bounds__(256) tversky_bwd_kernel(const float* __restrict__ mask, const double* __restrict__ acc, const float* __restrict__ gscale,
+                                                          long long S, float eps, float alpha_empty, float beta, float gamma,
+                                                          float* __restrict__ dpred) {
+  const int b = blockIdx.y;
+  const float* m = mask + (long long)b * S;
+  float* d = dpred + (long long)b * S;
+  const double tp = acc[b * 5 + 0], fp = acc[b * 5 + 1] - tp, fn = acc[b * 5 + 2] - tp;
+  const double num = tp + eps, den = tp + (double)beta * fn + (double)gamma * fp + eps;
+  const float a = (acc[b * 5 + 3] > 0.0) ? 1.f : alpha_empty;
+  const float c = gscale[b] * a;
+  // the gradient is affine in m: g = k0 + k1 * m
+  const float k0 = c * (float)(num * gamma / (den * den));
+  const float k1 = c * (float)((num * (1.0 - (double)beta - (double)gamma) - den) / (den * den));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x) d[i] = fmaf(k1, m[i], k0);
+}
+
 // ---- InfoNCE family ------------------------------------------------------------------------------------------------------
 // rows P[rows][E] -> Pn = P / max(||P||, eps), invn = 1 / max(||P||, eps). One warp per row.
 __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ P, float* __restrict__ Pn, float* __restrict__ invn, int rows, int E,
@@ -495,6 +531,32 @@ int ich_seg_loss_bwd(const float* pred, const float* mask, const double* acc, co
   if (bx < 1) bx = 1;
   seg_loss_bwd_kernel<<<dim3(bx, B), 256, 0, s>>>(pred, mask, acc, gscale, S, P, eps, alpha_empty, w_bce, w_dice, beta, w_bce != 0.f, dpred);
   return ich_check_launch("ich_seg_loss_bwd");
+}
+
+int ich_tversky_loss_fwd(const float* pred, const float* mask, int B, long long S, float eps, float alpha_empty, float beta, float gamma,
+                         int reduction, double* acc /*[B*5]*/, float* per_sample /*[B]*/, float* loss /*[1]*/, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(B > 0 && B <= 65535, "ich_tversky_loss_fwd: batch %d out of range", B);
+  cudaMemsetAsync(acc, 0, sizeof(double) * 5 * B, s);
+  int bx = (int)((S + 256 * 8 - 1) / (256 * 8));
+  int cap = (ich_num_sms() * 8 + B - 1) / B;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  seg_loss_reduce_kernel<<<dim3(bx, B), 256, 0, s>>>(pred, mask, S, 1.f, 0.f, 0, acc);
+  tversky_finalize_kernel<<<1, 256, 0, s>>>(acc, B, eps, alpha_empty, beta, gamma, reduction, per_sample, loss);
+  return ich_check_launch("ich_tversky_loss_fwd");
+}
+
+int ich_tversky_loss_bwd(const float* mask, const double* acc, const float* gscale /*[B]*/, int B, long long S, float eps, float alpha_empty,
+                         float beta, float gamma, float* dpred, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(B > 0 && B <= 65535, "ich_tversky_loss_bwd: batch %d out of range", B);
+  int bx = (int)((S + 256 * 4 - 1) / (256 * 4));
+  int cap = (ich_num_sms() * 8 + B - 1) / B;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  tversky_bwd_kernel<<<dim3(bx, B), 256, 0, s>>>(mask, acc, gscale, S, eps, alpha_empty, beta, gamma, dpred);
+  return ich_check_launch("ich_tversky_loss_bwd");
 }
 
 // P: [B][R][E] fp32 (R = 2 * set size). Outputs: Pn [B][R][E], invn [B*R], lse [B*R], rowloss [B*R], loss [1]; counter: zeroed u32.

@@ -821,6 +821,43 @@ class SegLoss(Function):
         return dpred, None, None, None, None, None, None, None, None
 
 
+class TverskyLossFn(Function):
+    """TverskyLoss (models/optim/LossFunctions.py:65-114): the Dice reduction pass (TP, sum p, sum m per sample in fp64) + a
+    finalize; the gradient is affine in the mask, so the backward pass reads only the mask."""
+
+    @staticmethod
+    def forward(ctx, pred, mask, eps, alpha_empty, beta, gamma, reduction):
+        _require_cuda(pred, 'TverskyLoss')
+        pred_c = pred.contiguous().float()
+        mask_c = mask.detach().contiguous().float()
+        b = pred_c.shape[0]
+        s = pred_c.numel() // b
+        acc = torch.empty((b, 5), dtype=torch.float64, device=pred.device)
+        per = torch.empty(b, dtype=torch.float32, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        call('ich_tversky_loss_fwd', pred_c.data_ptr(), mask_c.data_ptr(), b, s, float(eps), float(alpha_empty), float(beta), float(gamma),
+             _RED[reduction], acc.data_ptr(), per.data_ptr(), loss.data_ptr(), _stream())
+        ctx.save_for_backward(mask_c, acc)
+        ctx.args = (float(eps), float(alpha_empty), float(beta), float(gamma), reduction, pred.shape)
+        return per if reduction == 'none' else loss
+
+    @staticmethod
+    def backward(ctx, g):
+        mask, acc = ctx.saved_tensors
+        eps, alpha_empty, beta, gamma, reduction, shape = ctx.args
+        b = mask.shape[0]
+        s = mask.numel() // b
+        g = g.float()
+        if reduction == 'none':
+            gscale = g.contiguous()
+        else:
+            gscale = (g / b if reduction == 'mean' else g).expand(b).contiguous()
+        dpred = torch.empty(shape, dtype=torch.float32, device=mask.device)
+        call('ich_tversky_loss_bwd', mask.data_ptr(), acc.data_ptr(), gscale.data_ptr(), b, s, eps, alpha_empty, beta, gamma,
+             dpred.data_ptr(), _stream())
+        return dpred, None, None, None, None, None, None
+
+
 class InfoNCE(Function):
     """mean_rows( logsumexp_{j != i} S_ij - S_{i, pos(i)} ), S = cos / tau, on P [B][2A][E] (closed form of
     models/optim/LossFunctions.py:208-230 and :328-339)."""

@@ -21,6 +21,17 @@ def binary_dice_loss(pred, mask, reduction='mean', p=2, alpha=1.0, eps=1):
     return _reduce(dl, reduction)
 
 
+def tversky_loss(pred, mask, alpha=1.0, beta=0.5, gamma=0.5, reduction='mean', eps=1):
+    """TverskyLoss.forward, LossFunctions.py:88-114."""
+    dims = tuple(range(1, pred.ndim))
+    tp = (pred * mask).sum(dims)                                               # :101
+    fp = (pred * (1 - mask)).sum(dims)                                         # :102
+    fn = ((1 - pred) * mask).sum(dims)                                         # :103
+    tl = 1 - (tp + eps) / (tp + beta * fn + gamma * fp + eps)                  # :105
+    tl = torch.where(mask.sum(dims) > 0, tl, alpha * tl)                       # :107
+    return _reduce(tl, reduction)
+
+
 def combo_loss(pred, mask, alpha=0.5, beta=0.5, reduction='mean', p=1):
     """ComboLoss.forward, LossFunctions.py:143-166 (BCE summed over voxels, :157)."""
     dims = tuple(range(1, pred.ndim))

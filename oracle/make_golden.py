@@ -55,6 +55,25 @@ def bilinear_fixtures(ref_unet, ref_loss, UO, LO, report):
     torch.save(cases, os.path.join(OUT, 'unet_bilinear.pt'))
 
 
+def tversky_fixtures(ref_loss, LO, report):
+    """TverskyLoss known-answer vectors (values + input gradients) from the reference module -> tests/golden/tversky.pt."""
+    g = torch.Generator().manual_seed(9)
+    pred = torch.rand(4, 1, 4, 8, 8, generator=g)
+    mask = (torch.rand(4, 1, 4, 8, 8, generator=g) > 0.8).float()
+    mask[1] = 0                      # empty mask -> alpha scaling
+    mask[3] = 1                      # full mask
+    pred[0, 0, 0, 0, :2] = torch.tensor([0.0, 1.0])
+    cases = []
+    for lk in [dict(alpha=1.0, beta=0.5, gamma=0.5, reduction='mean'), dict(alpha=0.2, beta=0.7, gamma=0.3, reduction='none'),
+               dict(alpha=0.5, beta=0.3, gamma=0.9, reduction='sum'), dict(alpha=0.0, beta=1.0, gamma=0.0, reduction='mean')]:
+        p = pred.clone().requires_grad_(True)
+        v = ref_loss.TverskyLoss(**lk)(p, mask)
+        v.sum().backward()
+        cases.append(dict(kwargs=lk, value=v.detach(), grad=p.grad.clone()))
+        report[f'TverskyLoss {lk}'] = ((LO.tversky_loss(pred, mask, **lk) - v).abs().max() / v.abs().max().clamp_min(1e-12)).item()
+    torch.save(dict(pred=pred, mask=mask, cases=cases), os.path.join(OUT, 'tversky.pt'))
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import unet_oracle as UO, losses_oracle as LO
@@ -62,8 +81,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
     report = {}
-    if '--bilinear-only' in sys.argv:      # add the bilinear fixtures without rewriting the others
-        bilinear_fixtures(ref_unet, ref_loss, UO, LO, report)
+    if '--bilinear-only' in sys.argv or '--tversky-only' in sys.argv:      # add fixtures without rewriting the others
+        if '--bilinear-only' in sys.argv:
+            bilinear_fixtures(ref_unet, ref_loss, UO, LO, report)
+        else:
+            tversky_fixtures(ref_loss, LO, report)
         for k, v in report.items():
             print(f'{k:60s} oracle-vs-reference {v:.3e}')
         assert max(report.values()) < 5e-5
@@ -213,6 +235,7 @@ def main():
     torch.save(dict(pred=pred, mask=mask, cases=cases, infonce=nce, local=loc), os.path.join(OUT, 'losses.pt'))
 
     bilinear_fixtures(ref_unet, ref_loss, UO, LO, report)
+    tversky_fixtures(ref_loss, LO, report)
 
     worst = 0.0
     for k, v in report.items():

@@ -77,6 +77,17 @@ def test_loss_vectors(golden):
         assert abs(LO.local_info_nce_loss(c['f1'], c['f2'], c['tau'], c['K'], c['n_region']).item() - c['value'].item()) < 5e-6
 
 
+def test_tversky_vectors(golden):
+    """TverskyLoss (LossFunctions.py:65-114): oracle vs the reference module's values and input gradients."""
+    fx = golden('tversky.pt')
+    for c in fx['cases']:
+        p = fx['pred'].clone().requires_grad_(True)
+        v = LO.tversky_loss(p, fx['mask'], **c['kwargs'])
+        assert v.shape == c['value'].shape and torch.allclose(v, c['value'], rtol=1e-6, atol=1e-7)
+        v.sum().backward()
+        assert torch.allclose(p.grad, c['grad'], rtol=1e-5, atol=1e-8)
+
+
 def test_sliding_window_identity():
     """Non-overlapping windows == whole-volume eval forward when the window tiles the volume exactly is NOT true in
     general (zero padding at window borders), but a single window covering the volume must be the identity."""

@@ -358,6 +358,34 @@ def test_seg_losses_against_reference_vectors(golden):
         assert rel(p.grad, c['grad']) < 1e-4, c['kwargs']
 
 
+def test_tversky_loss_against_reference_vectors(golden):
+    """TverskyLoss on the engine vs the reference module (values 1e-5, input gradients 1e-4 relative); also the full-size shape
+    against the oracle on CPU (the fp32 reference sums 1 M terms per sample: 1e-4)."""
+    from src.models.optim import LossFunctions as LF
+    fx = golden('tversky.pt')
+    for c in fx['cases']:
+        p = fx['pred'].to(DEV).requires_grad_(True)
+        m = fx['mask'].to(DEV).requires_grad_(True)
+        v = LF.TverskyLoss(**c['kwargs'])(p, m)
+        assert v.shape == c['value'].shape
+        assert rel(v, c['value']) < 1e-5, c['kwargs']
+        v.sum().backward()
+        assert rel(p.grad, c['grad']) < 1e-4, c['kwargs']
+    g = torch.Generator().manual_seed(3)
+    pred = torch.rand(2, 1, 64, 128, 128, generator=g)
+    mask = (torch.rand(2, 1, 64, 128, 128, generator=g) > 0.98).float()
+    pc = pred.clone().requires_grad_(True)
+    ref = LO.tversky_loss(pc, mask, alpha=0.2, beta=0.7, gamma=0.3)
+    ref.backward()
+    pg = pred.to(DEV).requires_grad_(True)
+    out = LF.TverskyLoss(alpha=0.2, beta=0.7, gamma=0.3)(pg, mask.to(DEV))
+    out.backward()
+    assert abs(out.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert rel(pg.grad, pc.grad) < 1e-4
+    with pytest.raises(RuntimeError):                       # no CPU fallback
+        LF.TverskyLoss()(pred[:1], mask[:1])
+
+
 def test_infonce_against_reference_vectors(golden):
     from src.models.optim import LossFunctions as LF
     fx = golden('losses.pt')
