@@ -26,6 +26,7 @@ NET_KW = dict(depth=4, use_3D=True, in_channels=1, out_channels=1, top_filter=32
 LOSS_KW = dict(alpha=0.5, beta=0.5, reduction='mean', p=1)
 BATCH, PATCH = 8, (64, 128, 128)
 WORKLOAD = 'cfg-3: 3D U-Net depth4 tf32 mcf2, batch 8/GPU of 1x64x128x128, ComboLoss(Dice+BCE), Adam'
+METRIC = '3D U-Net fwd+bwd voxels/s'      # BASELINE.json `metric` (the tensor-pipe part is the `roofline` object)
 CONV_FLOP_PER_STEP = 9118.5e9            # SURVEY section 8d, algorithmic 2*M*N*K x3 (fwd + dgrad + wgrad), per GPU-step
 
 
@@ -173,7 +174,7 @@ def run_reference(args, emit):
     dt = time.perf_counter() - t0
     value = vox * args.steps / dt
     sample = f'batch 1 of 1x32x128x128 (1/16 of the per-GPU batch) per step, {threads} threads, torch CPU fp32'
-    line = {'impl': 'reference', 'metric': 'train_voxels_per_s', 'value': value, 'unit': 'voxels/s', 'n_gpus': args.gpus, 'steps': args.steps,
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'voxels/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'reference_sample': sample},
             'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port', 'sample': sample},
@@ -298,7 +299,7 @@ def main():
 
     if rank == 0:
         line = {
-            'metric': 'train_voxels_per_s', 'value': vox_step * args.steps / t_dev, 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
+            'metric': METRIC, 'value': vox_step * args.steps / t_dev, 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': world * args.batch, 'parallelism': f'dp{world}',
