@@ -153,6 +153,17 @@ int ich_head_dlogit(const float* out, const float* dout, void* dl, int dtype, in
 int ich_head1_bwd(const void* x, int x_ld, int dtype, const float* w, const float* out, const float* dout, void* dx, int dx_ld, float* dw,
                   float* db, long long M, int Cin, int act, void* stream);
 
+/* ---- last ConvBlock unit fused with the single-class head (models/networks/UNet.py:173-174 then :122): z = ReLU(BN(y)) is never
+ *      materialised.  fwd: out[m] = act(b + sum_c w[c] * relu(y[m][c] * scale[c] + shift[c])); bwd: d(logit) from out / dout, dz = d(logit) * w
+ *      rebuilt inside the two BatchNorm-backward passes -> dy, d(gamma), d(beta) and the head's d(w), d(b).  act: 0 none, 1 sigmoid.
+ *      sums: workspace of ICH_BN_SUM_COPIES * (3 * C + 1) doubles. ------------------------------------------------------------------- */
+int ich_bn_head_supported(int dtype, int C);
+int ich_bn_head_fwd(const void* y, int y_ld, int dtype, const float* scale, const float* shift, const float* w, const float* b, float* out,
+                    long long M, int C, int relu, int act, void* stream);
+int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, const float* shift, const float* mean, const float* invstd,
+                    const float* w, const float* out, const float* dout, double* sums, void* dy, int dy_ld, float* dgamma, float* dbeta,
+                    float* dw, float* db, long long M, int C, int relu, int training, int act, void* stream);
+
 /* ---- BinaryDiceLoss / ComboLoss (models/optim/LossFunctions.py:39-63,143-166) ---------------------------------------- */
 int ich_seg_loss_fwd(const float* pred, const float* mask, int B, long long S, float P, float eps, float alpha_empty, float w_bce, float w_dice,
                      float beta, int reduction, double* acc, float* per_sample, float* loss, void* stream);

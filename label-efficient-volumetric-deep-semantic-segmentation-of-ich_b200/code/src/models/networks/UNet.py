@@ -92,6 +92,18 @@ class ConvBlock(nn.Module):
         x = self._unit(x, self.conv1, self.bn1)
         return self._unit(x, self.conv2, self.bn2, concat_c, drop_p)
 
+    def forward_cl_head(self, x, final_conv, act):
+        """This block followed by the single-class head `final_conv` (+ Sigmoid if act == 1), with the second unit and the head fused
+        (ops.ConvBnReluHead; the caller checked ops.head_fusable).  Returns the network output, fp32 [N, 1, D, H, W]."""
+        x = self._unit(x, self.conv1, self.bn1)
+        conv, bn = self.conv2, self.bn2
+        training = self.training or not bn.track_running_stats
+        out = ops.ConvBnReluHead.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                                       final_conv.weight, final_conv.bias, act)
+        if training and bn.track_running_stats:
+            _PENDING_NBT.append(bn.num_batches_tracked)
+        return out
+
     def forward(self, input):
         was_4d = input.dim() == 4
         out = ops.from_channels_last(self.forward_cl(ops.to_channels_last(input)), was_4d)
@@ -193,12 +205,15 @@ class _UNetBase(nn.Module):
             res.append(skip)
         return self.bottleneck_block.forward_cl(x), res     # UNet.py:112
 
-    def _decode(self, x, res):
-        for up, block, r in zip(self.up_samp, self.up_block, res[::-1]):     # UNet.py:117-119
+    def _decode(self, x, res, head=None):
+        """head = (final_conv, act): the last block runs fused with the single-class head and the network output is returned."""
+        last = len(self.up_block) - 1
+        for i, (up, block, r) in enumerate(zip(self.up_samp, self.up_block, res[::-1])):     # UNet.py:117-119
             if isinstance(up, nn.Upsample):                                     # bilinear=True: UNet.py:69-72
-                x = block.forward_cl(ops.UpsampleCat.apply(x, r, self._fd))
-                continue
-            x = block.forward_cl(ops.UpConvCat.apply(x, r, up.weight, up.bias, self._fd, getattr(r, '_ich_concat_buf', None)))
+                x = ops.UpsampleCat.apply(x, r, self._fd)
+            else:
+                x = ops.UpConvCat.apply(x, r, up.weight, up.bias, self._fd, getattr(r, '_ich_concat_buf', None))
+            x = block.forward_cl_head(x, *head) if (head is not None and i == last) else block.forward_cl(x)
         return x
 
 
@@ -225,9 +240,14 @@ class UNet(_UNetBase):
         x = ops.to_channels_last(input)
         x, res = self._encode(x)
         x_bottleneck = x
-        x = self._decode(x, res)
         act = 0 if isinstance(self.final_activation, nn.Identity) else (2 if isinstance(self.final_activation, nn.Softmax) else 1)
-        out = ops.Head.apply(x, self.final_conv.weight, self.final_conv.bias, act)           # UNet.py:122
+        tail = self.up_block[-1] if len(self.up_block) else None
+        if tail is not None and not (tail.training and tail.dropout.p > 0.0) and tail.conv2.kernel_size[0] == 3 and \
+                ops.head_fusable(x.dtype, tail.conv2.out_channels, self.final_conv.weight, act, tail.training):
+            out = self._decode(x, res, head=(self.final_conv, act))                          # UNet.py:119 + :122, fused
+        else:
+            x = self._decode(x, res)
+            out = ops.Head.apply(x, self.final_conv.weight, self.final_conv.bias, act)       # UNet.py:122
         _flush_nbt()
         if was_4d:
             out = out.squeeze(2)

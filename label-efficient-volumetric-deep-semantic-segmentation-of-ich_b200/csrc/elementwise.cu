@@ -898,6 +898,233 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
   }
 }
 
+// ---- last ConvBlock unit fused with the single-class 1x1 head (reference models/networks/UNet.py:122 after :173-174) -----------------
+// z = ReLU(BN(y)) of the last decoder unit is consumed by final_conv only, so it is never materialised: the head reads the conv
+// output y (BN + ReLU applied in registers), and the backward pass derives dz = d(logit) * w_head on the fly inside the two
+// BatchNorm-backward passes (which read y anyway).  Saves the z write + read, the dz write + two dz reads and one kernel per
+// direction.  Row layout as in the *_rows_kernel family: a thread owns one 16-byte channel group, the `groups` = C / V lanes of a
+// voxel are adjacent lanes of one warp (groups is a power of two <= 32).
+template <typename T>
+__global__ void __launch_bounds__(256) bn_head_fwd_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift, const float* __restrict__ w,
+                                                               const float* __restrict__ b, float* __restrict__ out, long long M, int C, int relu,
+                                                               int act) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = 4;                       // rows in flight per thread
+  const int groups = C / V, rpb = 256 / groups;
+  const int gi = threadIdx.x % groups, c = gi * V;
+  float sc[V], sf[V], wk[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { sc[k] = scale[c + k]; sf[k] = shift[c + k]; wk[k] = w[c + k]; }
+  const float bias = b ? b[0] : 0.f;
+  const long long step = (long long)gridDim.x * rpb;
+  // the trip count is uniform over the block (the shuffles below need whole warps); rows past M are masked
+  for (long long base = (long long)blockIdx.x * rpb; base < M; base += U * step) {
+    float a[U][V];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = base + u * step + threadIdx.x / groups;
+      valid[u] = r < M;
+      if (valid[u]) Vec<T>::load(y + r * y_ld + c, a[u]);
+      else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) a[u][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float p = 0.f;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float z = fmaf(a[u][k], sc[k], sf[k]);
+        if (relu) z = fmaxf(z, 0.f);
+        p = fmaf(z, wk[k], p);
+      }
+      for (int o = 1; o < groups; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (valid[u] && gi == 0) {
+        p += bias;
+        out[base + u * step + threadIdx.x / groups] = act == 1 ? 1.f / (1.f + expf(-p)) : p;
+      }
+    }
+  }
+}
+
+// Reduction pass: d(beta) = sum dz, d(gamma) = sum dz * yhat (into the replicated fp64 `sums` of the BN-backward kernels) and the head's
+// d(w) = sum z * dl, d(b) = sum dl (into `hsums`, [BN_COPIES][C + 1] fp64), with dl = d(logit) and dz = dl * w_head * [z > 0].
+template <typename T>
+__global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                      const float* __restrict__ invstd, const float* __restrict__ w,
+                                                                      const float* __restrict__ out, const float* __restrict__ dout, long long M,
+                                                                      int C, int relu, int act, double* __restrict__ sums,
+                                                                      double* __restrict__ hsums) {
+  constexpr int V = Vec<T>::N;
+  constexpr int U = 4;
+  const int groups = C / V, rpb = 256 / groups;
+  const int gi = threadIdx.x % groups, c = gi * V;
+  float sc[V], sf[V], mu[V], is[V], wk[V], sb[V], sg[V], gw[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    sc[k] = scale[c + k]; sf[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; wk[k] = w[c + k];
+    sb[k] = sg[k] = gw[k] = 0.f;
+  }
+  float gb = 0.f;
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
+  for (; r + (U - 1) * step < M; r += U * step) {
+    float a[U][V], dl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      Vec<T>::load(y + (r + u * step) * y_ld + c, a[u]);
+      const float p = out[r + u * step], g = dout[r + u * step];
+      dl[u] = act == 1 ? g * p * (1.f - p) : g;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (gi == 0) gb += dl[u];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float z = fmaf(a[u][k], sc[k], sf[k]);
+        const bool pos = !relu || z > 0.f;
+        gw[k] = fmaf(dl[u], pos ? z : 0.f, gw[k]);
+        const float g0 = pos ? dl[u] * wk[k] : 0.f;
+        sb[k] += g0;
+        sg[k] = fmaf(g0, (a[u][k] - mu[k]) * is[k], sg[k]);
+      }
+    }
+  }
+  for (; r < M; r += step) {
+    float a0[V];
+    Vec<T>::load(y + r * y_ld + c, a0);
+    const float p = out[r], g = dout[r];
+    const float dl = act == 1 ? g * p * (1.f - p) : g;
+    if (gi == 0) gb += dl;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float z = fmaf(a0[k], sc[k], sf[k]);
+      const bool pos = !relu || z > 0.f;
+      gw[k] = fmaf(dl, pos ? z : 0.f, gw[k]);
+      const float g0 = pos ? dl * wk[k] : 0.f;
+      sb[k] += g0;
+      sg[k] = fmaf(g0, (a0[k] - mu[k]) * is[k], sg[k]);
+    }
+  }
+  // lanes that own the same channel group are `groups` apart: butterfly over those, one row of partials per warp, sum over the warps
+  extern __shared__ float sh[];  // [8 warps][3][C] + [8]
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < V; ++k)
+    for (int o = groups; o < 32; o <<= 1) {
+      sb[k] += __shfl_xor_sync(0xffffffffu, sb[k], o);
+      sg[k] += __shfl_xor_sync(0xffffffffu, sg[k], o);
+      gw[k] += __shfl_xor_sync(0xffffffffu, gw[k], o);
+    }
+  gb = warp_sum(gb);
+  if (lane < groups) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      sh[(wrp * 3 + 0) * C + c + k] = sb[k];
+      sh[(wrp * 3 + 1) * C + c + k] = sg[k];
+      sh[(wrp * 3 + 2) * C + c + k] = gw[k];
+    }
+  }
+  if (lane == 0) sh[8 * 3 * C + wrp] = gb;
+  __syncthreads();
+  const int copy = blockIdx.x % BN_COPIES;
+  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+    const int j = i / C, ch = i - j * C;
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += sh[(wq * 3 + j) * C + ch];
+    if (j < 2) atomicAdd(&sums[(size_t)copy * 2 * C + i], (double)t);
+    else atomicAdd(&hsums[(size_t)copy * (C + 1) + ch], (double)t);
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += sh[8 * 3 * C + wq];
+    atomicAdd(&hsums[(size_t)copy * (C + 1) + C], (double)t);
+  }
+}
+
+// Apply pass: dy = scale * (dz - d(beta)/M - yhat * d(gamma)/M) with dz rebuilt from d(logit); block 0 also publishes d(gamma),
+// d(beta) and the head's d(w), d(b).
+template <typename T>
+__global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd, const float* __restrict__ w,
+                                                                     const float* __restrict__ out, const float* __restrict__ dout,
+                                                                     const double* __restrict__ sums, const double* __restrict__ hsums,
+                                                                     T* __restrict__ dy, int dy_ld, long long M, int C, int relu, int training, int act,
+                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw,
+                                                                     float* __restrict__ db) {
+  constexpr int V = Vec<T>::N;
+  const int groups = C / V, rpb = 256 / groups;
+  const int c = (threadIdx.x % groups) * V;
+  const float invM = training ? (float)(1.0 / (double)M) : 0.f;
+  extern __shared__ float tot[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tot[i] = (float)bn_total(sums, i, C);
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      if (dbeta) dbeta[i] = tot[i];
+      if (dgamma) dgamma[i] = tot[C + i];
+    }
+    for (int i = threadIdx.x; i <= C; i += blockDim.x) {
+      double t = 0.0;
+      for (int k = 0; k < BN_COPIES; ++k) t += hsums[(size_t)k * (C + 1) + i];
+      if (i < C) { if (dw) dw[i] = (float)t; }
+      else if (db) db[0] = (float)t;
+    }
+  }
+  float sc[V], sf[V], k0[V], k1[V], wk[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    sc[k] = scale[c + k]; sf[k] = shift[c + k]; wk[k] = w[c + k];
+    k1[k] = sc[k] * invstd[c + k] * tot[C + c + k] * invM;
+    k0[k] = sc[k] * tot[c + k] * invM - mean[c + k] * k1[k];
+  }
+  const long long step = (long long)gridDim.x * rpb;
+  long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
+  for (; r + step < M; r += 2 * step) {
+    float b0[V], b1[V];
+    Vec<T>::load(y + r * y_ld + c, b0);
+    Vec<T>::load(y + (r + step) * y_ld + c, b1);
+    const float p0 = out[r], q0 = dout[r], p1 = out[r + step], q1 = dout[r + step];
+    const float dl0 = act == 1 ? q0 * p0 * (1.f - p0) : q0, dl1 = act == 1 ? q1 * p1 * (1.f - p1) : q1;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? dl0 * wk[k] : 0.f;
+      const float g1 = (!relu || fmaf(b1[k], sc[k], sf[k]) > 0.f) ? dl1 * wk[k] : 0.f;
+      b0[k] = fmaf(sc[k], g0, -fmaf(b0[k], k1[k], k0[k]));
+      b1[k] = fmaf(sc[k], g1, -fmaf(b1[k], k1[k], k0[k]));
+    }
+    Vec<T>::store(dy + r * dy_ld + c, b0);
+    Vec<T>::store(dy + (r + step) * dy_ld + c, b1);
+  }
+  if (r < M) {
+    float b0[V];
+    Vec<T>::load(y + r * y_ld + c, b0);
+    const float p0 = out[r], q0 = dout[r];
+    const float dl0 = act == 1 ? q0 * p0 * (1.f - p0) : q0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? dl0 * wk[k] : 0.f;
+      b0[k] = fmaf(sc[k], g0, -fmaf(b0[k], k1[k], k0[k]));
+    }
+    Vec<T>::store(dy + r * dy_ld + c, b0);
+  }
+}
+
+template <typename T>
+inline bool bn_head_ok(int C) {
+  const int V = Vec<T>::N;
+  if (C % V) return false;
+  const int groups = C / V;
+  return groups >= 1 && groups <= 32 && (groups & (groups - 1)) == 0;
+}
+
 }  // namespace
 
 template <typename T, bool DROPV>
@@ -1216,6 +1443,46 @@ int ich_avgpool_bwd(const float* dout, void* dx, int ld, int dtype, int N, long 
   if (total == 0) return 0;
   DISPATCH_T(dtype, "ich_avgpool_bwd", { avgpool_bwd_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(dout, (T*)dx, ld, S, C, total); })
   return ich_check_launch("ich_avgpool_bwd");
+}
+
+// ---- last ConvBlock unit + single-class head, fused (see bn_head_*_rows_kernel) ---------------------------------------------------
+int ich_bn_head_supported(int dtype, int C) {
+  if (dtype == ICH_F32) return bn_head_ok<float>(C) ? 1 : 0;
+  if (dtype == ICH_BF16) return bn_head_ok<bf16>(C) ? 1 : 0;
+  return 0;
+}
+
+int ich_bn_head_fwd(const void* y, int y_ld, int dtype, const float* scale, const float* shift, const float* w, const float* b, float* out,
+                    long long M, int C, int relu, int act, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(act == 0 || act == 1, "ich_bn_head_fwd: activation %d (0 none, 1 sigmoid)", act);
+  ICH_REQUIRE(ich_bn_head_supported(dtype, C), "ich_bn_head_fwd: unsupported dtype %d / channel count %d", dtype, C);
+  if (M == 0) return 0;
+  DISPATCH_T(dtype, "ich_bn_head_fwd", {
+    ICH_REQUIRE(vec_ok<T>(y, y_ld, C), "ich_bn_head_fwd: rows must be 16-byte aligned (ld %d)", y_ld);
+    bn_head_fwd_rows_kernel<T><<<rows_grid(M, C, Vec<T>::N), 256, 0, s>>>((const T*)y, y_ld, scale, shift, w, b, out, M, C, relu, act);
+  })
+  return ich_check_launch("ich_bn_head_fwd");
+}
+
+int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, const float* shift, const float* mean, const float* invstd,
+                    const float* w, const float* out, const float* dout, double* sums /*[ICH_BN_SUM_COPIES*(3*C+1)] workspace*/, void* dy, int dy_ld,
+                    float* dgamma, float* dbeta, float* dw, float* db, long long M, int C, int relu, int training, int act, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  ICH_REQUIRE(act == 0 || act == 1, "ich_bn_head_bwd: activation %d (0 none, 1 sigmoid)", act);
+  ICH_REQUIRE(ich_bn_head_supported(dtype, C), "ich_bn_head_bwd: unsupported dtype %d / channel count %d", dtype, C);
+  cudaMemsetAsync(sums, 0, sizeof(double) * BN_COPIES * (3 * C + 1), s);
+  double* hsums = sums + (size_t)BN_COPIES * 2 * C;
+  if (M == 0) return 0;
+  DISPATCH_T(dtype, "ich_bn_head_bwd", {
+    ICH_REQUIRE(vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C), "ich_bn_head_bwd: rows must be 16-byte aligned (ld %d / %d)", y_ld, dy_ld);
+    const int grid = rows_grid(M, C, Vec<T>::N);
+    bn_head_bwd_reduce_rows_kernel<T><<<grid, 256, sizeof(float) * (8 * 3 * C + 8), s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C,
+                                                                                       relu, act, sums, hsums);
+    bn_head_bwd_apply_rows_kernel<T><<<grid, 256, sizeof(float) * 2 * C, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums,
+                                                                            (T*)dy, dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+  })
+  return ich_check_launch("ich_bn_head_bwd");
 }
 
 }  // extern "C"

@@ -101,7 +101,7 @@ def lib():
 
 
 # kernels launched per entry point (memsets not counted); everything else launches exactly one
-KERNELS_PER_CALL = {'ich_bn_act_bwd': 2, 'ich_bn_act_bwd_drop': 2, 'ich_seg_loss_fwd': 2, 'ich_tversky_loss_fwd': 2,
+KERNELS_PER_CALL = {'ich_bn_act_bwd': 2, 'ich_bn_act_bwd_drop': 2, 'ich_bn_head_bwd': 2, 'ich_seg_loss_fwd': 2, 'ich_tversky_loss_fwd': 2,
                     'ich_infonce_fwd': 2}
 LAUNCHES = {}
 

@@ -19,6 +19,9 @@ _state = {
     # global contrastive set: InfoNCELoss compares against the embeddings of ALL ranks (all-gather) instead of the
     # local batch only.  Default off = the reference's per-process semantics (each rank an independent replica of the loss).
     'global_nce': os.environ.get('ICH_B200_GLOBAL_NCE', '0') == '1',
+    # single-class heads (out_channels = 1): run the last ConvBlock unit fused with final_conv + Sigmoid (ops.ConvBnReluHead): the
+    # BN+ReLU output of that unit is never materialised and its gradient is rebuilt inside the BatchNorm-backward passes
+    'fuse_head': os.environ.get('ICH_B200_FUSE_HEAD', '0') == '1',
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

@@ -370,6 +370,48 @@ def from_channels_last(x, was_4d=False):
     return out.squeeze(2) if was_4d else out
 
 
+def _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var, training):
+    """Conv (bias skipped in training mode: BatchNorm cancels it) with the batch statistics taken in the conv epilogue where the
+    tcgen05 kernels apply, then bn_finalize.  Returns (y [pre-BN conv output], stats [scale, shift, mean, invstd], synced)."""
+    n, d, h, w, cin = x.shape
+    cout = weight.shape[0]
+    m = n * d * h * w
+    dev = x.device
+    # training: BatchNorm cancels the conv bias, so the kernel skips it and bn_finalize folds it into running_mean
+    stats = torch.empty((4, cout), dtype=torch.float32, device=dev)      # scale, shift, mean, invstd
+    sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
+    k = _ksize(weight)
+    var = _tc_variant(x, cin, cout, k) if (training and k[1] == 3) else 0
+    if var:
+        # tcgen05 conv with the batch statistics accumulated in its epilogue (no separate pass over y)
+        y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=dev)
+        xp, xld = _rows(x)
+        with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
+            call('ich_conv_tc_fwd_stats', xp, xld, _p(_pack(weight, 'conv_fwd_tc_s' if var == 2 else 'conv_fwd_tc')), y.data_ptr(), cout, sums[0].data_ptr(),
+                 sums[1].data_ptr(), n, d, h, w, cin, cout, *k, _stream())
+    elif training and _cin1_tc(x, cin, cout, k):
+        # first layer: tcgen05 im2col kernel, batch statistics fused the same way
+        y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=dev)
+        xp, xld = _rows(x)
+        with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
+            call('ich_conv_cin1_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd')), None, y.data_ptr(), cout, sums[0].data_ptr(), sums[1].data_ptr(),
+                 n, d, h, w, cout, k[0], 0, _stream())
+    else:
+        y = conv_forward(x, weight, None)
+        if training:
+            call('ich_colstats', y.data_ptr(), cout, _dt(y), m, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+    comm = _sync_bn_comm() if training else None
+    m_stat = m
+    if comm is not None:
+        # SyncBN: per-channel sum / sum of squares over ALL ranks (equal local batch sizes, as under the DP sampler)
+        comm[1](sums)
+        m_stat = m * comm[0]
+    call('ich_bn_finalize', sums[0].data_ptr(), sums[1].data_ptr(), m_stat, cout, _p(gamma), _p(beta), _p(bias), _p(running_mean),
+         _p(running_var), BN_MOMENTUM, BN_EPS, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+         int(training), _stream())
+    return y, stats, comm is not None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Conv -> BatchNorm -> ReLU  (one unit of ConvBlock.forward, models/networks/UNet.py:173-174)
 # ---------------------------------------------------------------------------------------------------------------
@@ -379,42 +421,11 @@ class ConvBnRelu(Function):
         """drop_p > 0: nn.Dropout(p) applied to the unit's output (reference UNet.py:175-176) fused into the BN-apply kernel; the
         mask is a function of (seed, voxel, channel) and is regenerated in backward.  The seed is drawn from torch's default CPU
         generator, so torch.manual_seed makes runs reproducible (UNet2D_scripts.py:53-60)."""
-        n, d, h, w, cin = x.shape
+        n, d, h, w, _ = x.shape
         cout = weight.shape[0]
         m = n * d * h * w
         dev = x.device
-        # training: BatchNorm cancels the conv bias, so the kernel skips it and bn_finalize folds it into running_mean
-        stats = torch.empty((4, cout), dtype=torch.float32, device=dev)      # scale, shift, mean, invstd
-        sums = torch.empty((2, cout), dtype=torch.float64, device=dev)
-        k = _ksize(weight)
-        var = _tc_variant(x, cin, cout, k) if (training and k[1] == 3) else 0
-        if var:
-            # tcgen05 conv with the batch statistics accumulated in its epilogue (no separate pass over y)
-            y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=dev)
-            xp, xld = _rows(x)
-            with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
-                call('ich_conv_tc_fwd_stats', xp, xld, _p(_pack(weight, 'conv_fwd_tc_s' if var == 2 else 'conv_fwd_tc')), y.data_ptr(), cout, sums[0].data_ptr(),
-                     sums[1].data_ptr(), n, d, h, w, cin, cout, *k, _stream())
-        elif training and _cin1_tc(x, cin, cout, k):
-            # first layer: tcgen05 im2col kernel, batch statistics fused the same way
-            y = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=dev)
-            xp, xld = _rows(x)
-            with _Timed('fwd', 2.0 * m * cin * cout * k[0] * k[1] * k[2]):
-                call('ich_conv_cin1_tc_fwd', xp, xld, _p(_pack(weight, 'conv_fwd')), None, y.data_ptr(), cout, sums[0].data_ptr(), sums[1].data_ptr(),
-                     n, d, h, w, cout, k[0], 0, _stream())
-        else:
-            y = conv_forward(x, weight, None)
-            if training:
-                call('ich_colstats', y.data_ptr(), cout, _dt(y), m, cout, sums[0].data_ptr(), sums[1].data_ptr(), _stream())
-        comm = _sync_bn_comm() if training else None
-        m_stat = m
-        if comm is not None:
-            # SyncBN: per-channel sum / sum of squares over ALL ranks (equal local batch sizes, as under the DP sampler)
-            comm[1](sums)
-            m_stat = m * comm[0]
-        call('ich_bn_finalize', sums[0].data_ptr(), sums[1].data_ptr(), m_stat, cout, _p(gamma), _p(beta), _p(bias), _p(running_mean),
-             _p(running_var), BN_MOMENTUM, BN_EPS, stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
-             int(training), _stream())
+        y, stats, synced = _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var, training)
         if concat_c:
             # zero-copy skip connection: z is written as the first channel slab of the [.., cout + concat_c] buffer that the
             # decoder's ConvTranspose later completes (torch.cat([res, up], 1) of reference UNet.py:119 without the copy)
@@ -436,7 +447,7 @@ class ConvBnRelu(Function):
                  _stream())
         ctx.save_for_backward(x, weight, y, stats)
         ctx.training, ctx.relu, ctx.drop = training, relu, (drop_p, seed)
-        ctx.sync = comm is not None
+        ctx.sync = synced
         if concat_c:
             ctx.mark_non_differentiable(buf)
             return z, buf
@@ -483,6 +494,63 @@ class ConvBnRelu(Function):
             # training: d(loss)/d(bias) is exactly 0 (BatchNorm removes the mean); eval: sum of dy
             db = torch.zeros(cout, dtype=torch.float32, device=y.device) if ctx.training else col_sum(dy).float()
         return dx, dw, db, (dgamma if need[3] else None), (dbeta if need[4] else None), None, None, None, None, None, None
+
+
+class ConvBnReluHead(Function):
+    """Last unit of the last decoder ConvBlock fused with the single-class head: Conv -> BN -> ReLU -> final 1x1 conv -> Sigmoid /
+    Identity (reference UNet.py:173-174 then :122).  z = ReLU(BN(y)) feeds final_conv only, so it is never written: the head kernel
+    reads the conv output y, and the backward rebuilds dz = d(logit) * w_head inside the two BatchNorm-backward passes.  Returns the
+    network output, fp32 [N, 1, D, H, W]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, training, head_weight, head_bias, act):
+        n, d, h, w, _ = x.shape
+        cout = weight.shape[0]
+        y, stats, synced = _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var, training)
+        if synced:
+            raise RuntimeError('ich_b200.ConvBnReluHead: not available with SyncBN (the caller must take the unfused path)')
+        out = torch.empty((n, 1, d, h, w), dtype=torch.float32, device=x.device)
+        hw = head_weight.detach().reshape(cout).float().contiguous()
+        call('ich_bn_head_fwd', y.data_ptr(), cout, _dt(y), stats[0].data_ptr(), stats[1].data_ptr(), hw.data_ptr(), _p(head_bias), out.data_ptr(),
+             n * d * h * w, cout, 1, act, _stream())
+        ctx.save_for_backward(x, weight, y, stats, hw, out)
+        ctx.training, ctx.act, ctx.head_shape = training, act, head_weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, y, stats, hw, out = ctx.saved_tensors
+        n, d, h, w, cout = y.shape
+        m = n * d * h * w
+        dev = y.device
+        dout = dout.contiguous().float()
+        dy = torch.empty_like(y)
+        sums = torch.empty(BN_SUM_COPIES * (3 * cout + 1), dtype=torch.float64, device=dev)
+        dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+        dhw = torch.empty(cout, dtype=torch.float32, device=dev)
+        dhb = torch.empty(1, dtype=torch.float32, device=dev)
+        call('ich_bn_head_bwd', y.data_ptr(), cout, _dt(y), stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(), stats[3].data_ptr(),
+             hw.data_ptr(), out.data_ptr(), dout.data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(),
+             dhw.data_ptr(), dhb.data_ptr(), m, cout, 1, int(ctx.training), ctx.act, _stream())
+        need = ctx.needs_input_grad
+        dx = conv_dgrad(dy, weight) if need[0] else None
+        dw = conv_wgrad(x, dy, weight) if need[1] else None
+        db = None
+        if need[2]:
+            db = torch.zeros(cout, dtype=torch.float32, device=dev) if ctx.training else col_sum(dy).float()
+        return (dx, dw, db, (dgamma if need[3] else None), (dbeta if need[4] else None), None, None, None,
+                (dhw.view(ctx.head_shape) if need[8] else None), (dhb if need[9] else None), None)
+
+
+def head_fusable(x_dtype, cout, head_weight, act, training):
+    """Can the last ConvBlock unit (cout channels) run fused with this head (ConvBnReluHead)?"""
+    if not config.get('fuse_head') or head_weight.shape[0] != 1 or head_weight[0, 0].numel() != 1 or act not in (0, 1):
+        return False
+    if training and _sync_bn_comm() is not None:
+        return False
+    from ._lib import lib
+    return bool(lib().ich_bn_head_supported(config.dtype_code(x_dtype), cout))
 
 
 class ConvBias(Function):

@@ -169,6 +169,96 @@ def test_sync_bn_two_emulated_ranks():
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('training', [True, False])
+@pytest.mark.parametrize('case', [(16, 32, 1, True), (32, 32, 0, True), (8, 16, 1, False), (16, 64, 1, True)])   # cin, cout, act, 3-D
+def test_conv_bn_relu_head_fused(prec, training, case):
+    """Last ConvBlock unit fused with the single-class head (ops.ConvBnReluHead) vs torch CPU: Conv -> BN -> ReLU -> 1x1 conv -> Sigmoid.
+    The BN+ReLU output is never materialised; its gradient is rebuilt inside the BN-backward passes."""
+    cin, cout, act, is3d = case
+    g = torch.Generator().manual_seed(11)
+    n, d, h, w = (2, 7, 16, 16) if is3d else (3, 1, 24, 40)      # odd row counts: the masked tail of the 4-rows-in-flight loops
+    x = torch.randn(n, cin, d, h, w, generator=g)
+    conv = torch.nn.Conv3d(cin, cout, 3 if is3d else (1, 3, 3), padding=1 if is3d else (0, 1, 1))
+    bn = torch.nn.BatchNorm3d(cout)
+    head = torch.nn.Conv3d(cout, 1, 1)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(0, 0.3, generator=g)
+        bn.running_mean.normal_(0, 0.2, generator=g); bn.running_var.uniform_(0.5, 1.5, generator=g)
+        head.weight.normal_(0, 0.3, generator=g)
+    dout = torch.randn(n, 1, d, h, w, generator=g)
+    if prec == 'bf16':
+        x = x.bfloat16().float()
+        with torch.no_grad():
+            conv.weight.copy_(conv.weight.bfloat16().float())
+    import copy
+    conv_c, bn_c, head_c = copy.deepcopy(conv).to(DEV), copy.deepcopy(bn).to(DEV), copy.deepcopy(head).to(DEV)
+    conv.train(training); bn.train(training)
+    xr = x.clone().requires_grad_(True)
+    ar = bn(conv(xr))
+    lr = head(F.relu(ar))
+    outr = torch.sigmoid(lr) if act == 1 else lr
+    # voxels with a knife-edge pre-activation in ANY channel get no upstream gradient (see test_conv_bn_relu_unit)
+    dout = dout * (ar.detach().abs().min(dim=1, keepdim=True).values > 2e-3)
+    outr.backward(dout)
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+        from ich_b200 import _lib
+        assert _lib.lib().ich_bn_head_supported(config.dtype_code(dt), cout) == 1
+        xc = cl(x, dt).requires_grad_(True)
+        wc = conv_c.weight if is3d else torch.nn.Parameter(conv_c.weight.detach()[:, :, 0].contiguous())
+        hw = head_c.weight if is3d else torch.nn.Parameter(head_c.weight.detach()[:, :, 0].contiguous())
+        out = ops.ConvBnReluHead.apply(xc, wc, conv_c.bias, bn_c.weight, bn_c.bias, bn_c.running_mean, bn_c.running_var, training, hw,
+                                       head_c.bias, act)
+        out.backward(dout.to(DEV))
+    tol = TOL[prec]
+    assert out.shape == outr.shape and out.dtype == torch.float32 and out.is_contiguous()
+    assert rel(out, outr) < tol
+    gt = tol if prec == 'fp32' else 6e-2
+    assert rel(nc(xc.grad), xr.grad) < gt
+    assert rel(wc.grad.reshape(conv.weight.shape), conv.weight.grad) < gt
+    assert rel(bn_c.weight.grad, bn.weight.grad) < gt and rel(bn_c.bias.grad, bn.bias.grad) < gt
+    assert rel(hw.grad.reshape(head.weight.shape), head.weight.grad) < gt and rel(head_c.bias.grad, head.bias.grad) < gt
+    if training:
+        assert conv_c.bias.grad.abs().max().item() == 0.0
+        assert rel(bn_c.running_mean, bn.running_mean) < tol and rel(bn_c.running_var, bn.running_var) < tol
+    else:
+        assert rel(conv_c.bias.grad, conv.bias.grad) < gt
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_fused_head_matches_unfused_path_at_size(prec):
+    """524 288 voxels (the unrolled main loops of the fused kernels, not only their tails): ops.ConvBnReluHead vs ops.ConvBnRelu +
+    ops.Head on the same device inputs.  Both paths derive the ReLU mask from the same conv output, so there are no mask flips; the
+    only difference is z / dz rounded to the activation dtype on the unfused path (fp32: 1e-4, bf16: 1e-2 north-star tolerance)."""
+    g = torch.Generator().manual_seed(5)
+    cin, cout = 16, 32
+    with config.override(precision=prec):
+        dt = config.act_dtype()
+        x = torch.randn(2, 16, 128, 128, cin, generator=g).to(DEV, dt)
+        dout = torch.randn(2, 1, 16, 128, 128, generator=g).to(DEV)
+        res = []
+        for fused in (False, True):
+            torch.manual_seed(1)
+            conv = torch.nn.Conv3d(cin, cout, 3, padding=1).to(DEV)
+            bn = torch.nn.BatchNorm3d(cout).to(DEV)
+            head = torch.nn.Conv3d(cout, 1, 1).to(DEV)
+            with torch.no_grad():
+                bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3); head.weight.normal_(0, 0.3)
+            xc = x.clone().requires_grad_(True)
+            args = (xc, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, True)
+            if fused:
+                out = ops.ConvBnReluHead.apply(*args, head.weight, head.bias, 1)
+            else:
+                out = ops.Head.apply(ops.ConvBnRelu.apply(*args, True), head.weight, head.bias, 1)
+            out.backward(dout)
+            res.append(dict(out=out, dx=xc.grad, dw=conv.weight.grad, dg=bn.weight.grad, db=bn.bias.grad, dhw=head.weight.grad,
+                            dhb=head.bias.grad, rm=bn.running_mean, rv=bn.running_var))
+    tol = TOL[prec]
+    for k in res[0]:
+        assert rel(res[1][k], res[0][k]) < tol, k
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
 @pytest.mark.parametrize('p', [0.5, 0.1])
 def test_fused_dropout_unit(prec, p):
     """nn.Dropout(p) after the unit (reference UNet.py:175-176), fused into the BN-apply / BN-backward kernels.  The mask is
@@ -490,12 +580,14 @@ def _grad_check(net, fx, tol, bias_abs):
     assert worst < tol, worst
 
 
-def test_unet3d_end_to_end_fp32(golden):
-    """fp32 verification mode vs the reference golden run: outputs / loss 1e-4, bit-exact masks, running stats, eval."""
+@pytest.mark.parametrize('fuse', [False, True])
+def test_unet3d_end_to_end_fp32(golden, fuse):
+    """fp32 verification mode vs the reference golden run: outputs / loss 1e-4, bit-exact masks, running stats, eval.
+    fuse: last ConvBlock unit + head as one op (ICH_B200_FUSE_HEAD)."""
     from src.models.networks.UNet import UNet
     from src.models.optim.LossFunctions import ComboLoss
     fx = golden('unet3d_combo.pt')
-    with config.override(precision='fp32'):
+    with config.override(precision='fp32', fuse_head=fuse):
         net = _load(UNet, fx)
         x = fx['x'].to(DEV).requires_grad_(True)
         m = fx['mask'].to(DEV).requires_grad_(True)
@@ -585,11 +677,12 @@ def test_zero_copy_concat_matches_copying_path(golden):
         assert rel(res[1][1][k], res[0][1][k]) < 1e-5 or res[0][1][k].abs().max() == 0, k
 
 
-def test_unet3d_end_to_end_bf16(golden):
+@pytest.mark.parametrize('fuse', [False, True])
+def test_unet3d_end_to_end_bf16(golden, fuse):
     from src.models.networks.UNet import UNet
     from src.models.optim.LossFunctions import ComboLoss
     fx = golden('unet3d_combo.pt')
-    with config.override(precision='bf16'):
+    with config.override(precision='bf16', fuse_head=fuse):
         net = _load(UNet, fx)
         out = net(fx['x'].to(DEV))
         loss = ComboLoss(**fx['loss_kwargs'])(out, fx['mask'].to(DEV))
@@ -601,11 +694,12 @@ def test_unet3d_end_to_end_bf16(golden):
         assert (dice((out >= 0.5).float().cpu(), mk) - dice((fx['out_train'] >= 0.5).float(), mk)).abs().max() < 1e-3
 
 
-def test_unet2d_end_to_end_fp32(golden):
+@pytest.mark.parametrize('fuse', [False, True])
+def test_unet2d_end_to_end_fp32(golden, fuse):
     from src.models.networks.UNet import UNet
     from src.models.optim.LossFunctions import BinaryDiceLoss
     fx = golden('unet2d_dice.pt')
-    with config.override(precision='fp32'):
+    with config.override(precision='fp32', fuse_head=fuse):
         net = _load(UNet, fx)
         out = net(fx['x'].to(DEV))
         loss = BinaryDiceLoss(**fx['loss_kwargs'])(out, fx['mask'].to(DEV))
