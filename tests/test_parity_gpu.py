@@ -196,6 +196,7 @@ def test_conv_bn_relu_head_fused(prec, training, case):
     xr = x.clone().requires_grad_(True)
     ar = bn(conv(xr))
     lr = head(F.relu(ar))
+    lr.retain_grad()
     outr = torch.sigmoid(lr) if act == 1 else lr
     # voxels with a knife-edge pre-activation in ANY channel get no upstream gradient (see test_conv_bn_relu_unit)
     dout = dout * (ar.detach().abs().min(dim=1, keepdim=True).values > 2e-3)
@@ -217,7 +218,10 @@ def test_conv_bn_relu_head_fused(prec, training, case):
     assert rel(nc(xc.grad), xr.grad) < gt
     assert rel(wc.grad.reshape(conv.weight.shape), conv.weight.grad) < gt
     assert rel(bn_c.weight.grad, bn.weight.grad) < gt and rel(bn_c.bias.grad, bn.bias.grad) < gt
-    assert rel(hw.grad.reshape(head.weight.shape), head.weight.grad) < gt and rel(head_c.bias.grad, head.bias.grad) < gt
+    assert rel(hw.grad.reshape(head.weight.shape), head.weight.grad) < gt
+    # d(head bias) = sum of d(logit) over all voxels: random signs cancel to ~1e-4 of sum |d(logit)|, so the error is measured
+    # against the magnitude of the summed terms, not against the cancelled result
+    assert (head_c.bias.grad.cpu() - head.bias.grad).abs().item() < gt * lr.grad.abs().sum().item() * 1e-2
     if training:
         assert conv_c.bias.grad.abs().max().item() == 0.0
         assert rel(bn_c.running_mean, bn.running_mean) < tol and rel(bn_c.running_var, bn.running_var) < tol
