@@ -904,13 +904,36 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 // BatchNorm-backward passes (which read y anyway).  Saves the z write + read, the dz write + two dz reads and one kernel per
 // direction.  Row layout as in the *_rows_kernel family: a thread owns one 16-byte channel group, the `groups` = C / V lanes of a
 // voxel are adjacent lanes of one warp (groups is a power of two <= 32).
+// 16-byte row chunks are kept as raw registers (4 per chunk) while in flight and widened to fp32 only when consumed, so that 8 rows
+// per thread can be outstanding (HBM needs ~64-96 KB in flight per SM; measured 3.4 TB/s with 4 widened rows, see profiles/).
+template <typename T> struct Raw16;
+template <> struct Raw16<float> {
+  typedef float4 R;
+  __device__ static R zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ static R load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static void unpack(const R& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+};
+template <> struct Raw16<bf16> {
+  typedef uint4 R;
+  __device__ static R zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static R load(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static void unpack(const R& t, float* v) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256) bn_head_fwd_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, 3) bn_head_fwd_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                                const float* __restrict__ shift, const float* __restrict__ w,
                                                                const float* __restrict__ b, float* __restrict__ out, long long M, int C, int relu,
                                                                int act) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = 4;                       // rows in flight per thread
+  constexpr int U = 8;                       // rows in flight per thread
   const int groups = C / V, rpb = 256 / groups;
   const int gi = threadIdx.x % groups, c = gi * V;
   float sc[V], sf[V], wk[V];
@@ -920,31 +943,28 @@ __global__ void __launch_bounds__(256) bn_head_fwd_rows_kernel(const T* __restri
   const long long step = (long long)gridDim.x * rpb;
   // the trip count is uniform over the block (the shuffles below need whole warps); rows past M are masked
   for (long long base = (long long)blockIdx.x * rpb; base < M; base += U * step) {
-    float a[U][V];
-    bool valid[U];
+    typename Raw16<T>::R raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = base + u * step + threadIdx.x / groups;
-      valid[u] = r < M;
-      if (valid[u]) Vec<T>::load(y + r * y_ld + c, a[u]);
-      else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) a[u][k] = 0.f;
-      }
+      raw[u] = r < M ? Raw16<T>::load(y + r * y_ld + c) : Raw16<T>::zero();
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      const long long r = base + u * step + threadIdx.x / groups;
+      float a[V];
+      Raw16<T>::unpack(raw[u], a);
       float p = 0.f;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float z = fmaf(a[u][k], sc[k], sf[k]);
+        float z = fmaf(a[k], sc[k], sf[k]);
         if (relu) z = fmaxf(z, 0.f);
         p = fmaf(z, wk[k], p);
       }
       for (int o = 1; o < groups; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-      if (valid[u] && gi == 0) {
+      if (r < M && gi == 0) {
         p += bias;
-        out[base + u * step + threadIdx.x / groups] = act == 1 ? 1.f / (1.f + expf(-p)) : p;
+        out[r] = act == 1 ? 1.f / (1.f + expf(-p)) : p;
       }
     }
   }
@@ -960,7 +980,7 @@ __global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* _
                                                                       int C, int relu, int act, double* __restrict__ sums,
                                                                       double* __restrict__ hsums) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = 4;
+  constexpr int U = 8;
   const int groups = C / V, rpb = 256 / groups;
   const int gi = threadIdx.x % groups, c = gi * V;
   float sc[V], sf[V], mu[V], is[V], wk[V], sb[V], sg[V], gw[V];
@@ -971,43 +991,35 @@ __global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* _
   }
   float gb = 0.f;
   const long long step = (long long)gridDim.x * rpb;
-  long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
-  for (; r + (U - 1) * step < M; r += U * step) {
-    float a[U][V], dl[U];
+  for (long long r0 = (long long)blockIdx.x * rpb + threadIdx.x / groups; r0 < M; r0 += U * step) {
+    typename Raw16<T>::R raw[U];
+    float dl[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      Vec<T>::load(y + (r + u * step) * y_ld + c, a[u]);
-      const float p = out[r + u * step], g = dout[r + u * step];
-      dl[u] = act == 1 ? g * p * (1.f - p) : g;
+      const long long r = r0 + u * step;
+      if (r < M) {
+        raw[u] = Raw16<T>::load(y + r * y_ld + c);
+        const float p = out[r], g = dout[r];
+        dl[u] = act == 1 ? g * p * (1.f - p) : g;
+      } else {               // masked row: dl = 0 contributes nothing to any sum
+        raw[u] = Raw16<T>::zero();
+        dl[u] = 0.f;
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      float a[V];
+      Raw16<T>::unpack(raw[u], a);
       if (gi == 0) gb += dl[u];
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float z = fmaf(a[u][k], sc[k], sf[k]);
+        const float z = fmaf(a[k], sc[k], sf[k]);
         const bool pos = !relu || z > 0.f;
         gw[k] = fmaf(dl[u], pos ? z : 0.f, gw[k]);
         const float g0 = pos ? dl[u] * wk[k] : 0.f;
         sb[k] += g0;
-        sg[k] = fmaf(g0, (a[u][k] - mu[k]) * is[k], sg[k]);
+        sg[k] = fmaf(g0, (a[k] - mu[k]) * is[k], sg[k]);
       }
-    }
-  }
-  for (; r < M; r += step) {
-    float a0[V];
-    Vec<T>::load(y + r * y_ld + c, a0);
-    const float p = out[r], g = dout[r];
-    const float dl = act == 1 ? g * p * (1.f - p) : g;
-    if (gi == 0) gb += dl;
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      const float z = fmaf(a0[k], sc[k], sf[k]);
-      const bool pos = !relu || z > 0.f;
-      gw[k] = fmaf(dl, pos ? z : 0.f, gw[k]);
-      const float g0 = pos ? dl * wk[k] : 0.f;
-      sb[k] += g0;
-      sg[k] = fmaf(g0, (a0[k] - mu[k]) * is[k], sg[k]);
     }
   }
   // lanes that own the same channel group are `groups` apart: butterfly over those, one row of partials per warp, sum over the warps
@@ -1060,6 +1072,7 @@ __global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __
                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw,
                                                                      float* __restrict__ db) {
   constexpr int V = Vec<T>::N;
+  constexpr int U = 4;
   const int groups = C / V, rpb = 256 / groups;
   const int c = (threadIdx.x % groups) * V;
   const float invM = training ? (float)(1.0 / (double)M) : 0.f;
@@ -1086,35 +1099,43 @@ __global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __
     k0[k] = sc[k] * tot[c + k] * invM - mean[c + k] * k1[k];
   }
   const long long step = (long long)gridDim.x * rpb;
-  long long r = (long long)blockIdx.x * rpb + threadIdx.x / groups;
-  for (; r + step < M; r += 2 * step) {
-    float b0[V], b1[V];
-    Vec<T>::load(y + r * y_ld + c, b0);
-    Vec<T>::load(y + (r + step) * y_ld + c, b1);
-    const float p0 = out[r], q0 = dout[r], p1 = out[r + step], q1 = dout[r + step];
-    const float dl0 = act == 1 ? q0 * p0 * (1.f - p0) : q0, dl1 = act == 1 ? q1 * p1 * (1.f - p1) : q1;
+  for (long long r0 = (long long)blockIdx.x * rpb + threadIdx.x / groups; r0 < M; r0 += U * step) {
+    typename Raw16<T>::R raw[U];
+    float dl[U];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      const float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? dl0 * wk[k] : 0.f;
-      const float g1 = (!relu || fmaf(b1[k], sc[k], sf[k]) > 0.f) ? dl1 * wk[k] : 0.f;
-      b0[k] = fmaf(sc[k], g0, -fmaf(b0[k], k1[k], k0[k]));
-      b1[k] = fmaf(sc[k], g1, -fmaf(b1[k], k1[k], k0[k]));
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * step;
+      if (r < M) {
+        raw[u] = Raw16<T>::load(y + r * y_ld + c);
+        const float p = out[r], g = dout[r];
+        dl[u] = act == 1 ? g * p * (1.f - p) : g;
+      } else {
+        raw[u] = Raw16<T>::zero();
+        dl[u] = 0.f;
+      }
     }
-    Vec<T>::store(dy + r * dy_ld + c, b0);
-    Vec<T>::store(dy + (r + step) * dy_ld + c, b1);
-  }
-  if (r < M) {
-    float b0[V];
-    Vec<T>::load(y + r * y_ld + c, b0);
-    const float p0 = out[r], q0 = dout[r];
-    const float dl0 = act == 1 ? q0 * p0 * (1.f - p0) : q0;
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      const float g0 = (!relu || fmaf(b0[k], sc[k], sf[k]) > 0.f) ? dl0 * wk[k] : 0.f;
-      b0[k] = fmaf(sc[k], g0, -fmaf(b0[k], k1[k], k0[k]));
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * step;
+      float a[V];
+      Raw16<T>::unpack(raw[u], a);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float g0 = (!relu || fmaf(a[k], sc[k], sf[k]) > 0.f) ? dl[u] * wk[k] : 0.f;
+        a[k] = fmaf(sc[k], g0, -fmaf(a[k], k1[k], k0[k]));
+      }
+      if (r < M) Vec<T>::store(dy + r * dy_ld + c, a);
     }
-    Vec<T>::store(dy + r * dy_ld + c, b0);
   }
+}
+
+// one wave of resident blocks: grid = #SMs x blocks that fit per SM (the kernels walk the rows with a grid-sized stride)
+template <typename K>
+inline int one_wave_grid(K kernel, size_t smem, long long M, int rpb) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 2;
+  long long blocks = (M + rpb - 1) / rpb, cap = (long long)ich_num_sms() * per_sm;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
 template <typename T>
@@ -1460,7 +1481,8 @@ int ich_bn_head_fwd(const void* y, int y_ld, int dtype, const float* scale, cons
   if (M == 0) return 0;
   DISPATCH_T(dtype, "ich_bn_head_fwd", {
     ICH_REQUIRE(vec_ok<T>(y, y_ld, C), "ich_bn_head_fwd: rows must be 16-byte aligned (ld %d)", y_ld);
-    bn_head_fwd_rows_kernel<T><<<rows_grid(M, C, Vec<T>::N), 256, 0, s>>>((const T*)y, y_ld, scale, shift, w, b, out, M, C, relu, act);
+    const int grid = one_wave_grid(bn_head_fwd_rows_kernel<T>, 0, M, 256 / (C / Vec<T>::N));
+    bn_head_fwd_rows_kernel<T><<<grid, 256, 0, s>>>((const T*)y, y_ld, scale, shift, w, b, out, M, C, relu, act);
   })
   return ich_check_launch("ich_bn_head_fwd");
 }
@@ -1476,11 +1498,14 @@ int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, cons
   if (M == 0) return 0;
   DISPATCH_T(dtype, "ich_bn_head_bwd", {
     ICH_REQUIRE(vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C), "ich_bn_head_bwd: rows must be 16-byte aligned (ld %d / %d)", y_ld, dy_ld);
-    const int grid = rows_grid(M, C, Vec<T>::N);
-    bn_head_bwd_reduce_rows_kernel<T><<<grid, 256, sizeof(float) * (8 * 3 * C + 8), s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C,
-                                                                                       relu, act, sums, hsums);
-    bn_head_bwd_apply_rows_kernel<T><<<grid, 256, sizeof(float) * 2 * C, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums,
-                                                                            (T*)dy, dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+    const int rpb = 256 / (C / Vec<T>::N);
+    const size_t sh_reduce = sizeof(float) * (8 * 3 * C + 8), sh_apply = sizeof(float) * 2 * C;
+    const int grid_r = one_wave_grid(bn_head_bwd_reduce_rows_kernel<T>, sh_reduce, M, rpb);
+    const int grid_a = one_wave_grid(bn_head_bwd_apply_rows_kernel<T>, sh_apply, M, rpb);
+    bn_head_bwd_reduce_rows_kernel<T><<<grid_r, 256, sh_reduce, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C, relu, act, sums,
+                                                                     hsums);
+    bn_head_bwd_apply_rows_kernel<T><<<grid_a, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
+                                                                   dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
   })
   return ich_check_launch("ich_bn_head_bwd");
 }
