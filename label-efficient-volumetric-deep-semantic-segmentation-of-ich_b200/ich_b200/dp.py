@@ -52,30 +52,37 @@ class GradAllReducer:
             b.pending = len(b.params)
 
     def _hook(self, p):
-        b, off = self._slot[p]
+        b, _ = self._slot[p]
         if not self._callback_queued:
             self._callback_queued = True
             torch.autograd.Variable._execution_engine.queue_callback(self._finish)
-        view = b.flat[off:off + p.numel()].view_as(p)
-        if p.grad.data_ptr() != view.data_ptr():
-            view.copy_(p.grad)
-            p.grad = view                       # the gradient now aliases the bucket: the all-reduce updates it in place
         b.pending -= 1
         if b.pending == 0:
-            op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == 'nccl') else dist.ReduceOp.SUM
-            b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
-            b.avg_done = op == dist.ReduceOp.AVG
+            self._launch(b)
+
+    def _launch(self, b):
+        """Gather the bucket's gradients into its flat buffer with ONE multi-tensor copy (not one copy kernel per parameter), make
+        the gradients alias the buffer, and start the all-reduce.  Parameters without a gradient this step (frozen / unused)
+        contribute zeros and keep `grad = None`."""
+        src, dst = [], []
+        for p, off in zip(b.params, b.offsets):
+            view = b.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                view.zero_()
+            elif p.grad.data_ptr() != view.data_ptr():
+                src.append(p.grad)
+                dst.append(view)
+                p.grad = view                   # the gradient now aliases the bucket: the all-reduce updates it in place
+        if src:
+            torch._foreach_copy_(dst, src)
+        op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == 'nccl') else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+        b.avg_done = op == dist.ReduceOp.AVG
 
     def _finish(self):
         for b in self.buckets:
-            if b.pending != 0:
-                # parameters that received no gradient this step (frozen / unused): reduce what is there
-                for p, off in zip(b.params, b.offsets):
-                    if p.grad is None:
-                        b.flat[off:off + p.numel()].zero_()
-                op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == 'nccl') else dist.ReduceOp.SUM
-                b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
-                b.avg_done = op == dist.ReduceOp.AVG
+            if b.pending != 0:                  # some parameters received no gradient this step: reduce what is there
+                self._launch(b)
             b.work.wait()
             if self.average and not b.avg_done:
                 b.flat.div_(self.world)

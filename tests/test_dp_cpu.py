@@ -55,6 +55,20 @@ def _worker(rank, world, port, out):
                 want /= world
                 assert torch.allclose(p_l, want, atol=1e-6), (step, (p_l - want).abs().max())
             opt.step()
+        # a frozen parameter (transfer_weights + requires_grad = False, models/optim/Contrastive.py:251-253): its bucket never
+        # completes through the hooks, is reduced at the end of backward with zeros in its slot, and its grad stays None
+        net[0].bias.requires_grad = False
+        opt.zero_grad()
+        torch.manual_seed(rank * 10 + 7)
+        x = torch.rand(2, 1, 4, 8, 8)
+        net(x).mean().backward()
+        assert net[0].bias.grad is None
+        want = net[0].weight.grad.detach().clone()          # already averaged: identical on both ranks
+        g = [torch.zeros_like(want) for _ in range(world)]
+        dist.all_gather(g, want)
+        assert torch.equal(g[0], g[1]) and want.abs().sum() > 0
+        opt.step()
+        net[0].bias.requires_grad = True
         # parameters stay identical across ranks after the steps
         for p in net.parameters():
             g = [torch.zeros_like(p) for _ in range(world)]
