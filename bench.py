@@ -255,8 +255,9 @@ def main():
 
     for _ in range(args.warmup):
         step(xd, md)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if rank == 0 else None      # one NVML poller per job, not one per rank
+    if sampler is not None:
+        sampler.start()
     l0 = _lib.launches()
     t_dev = timed(lambda: step(xd, md), args.steps)
     launches = _lib.launches() - l0
@@ -287,8 +288,9 @@ def main():
             step(x, m).item()
     e2e_run()
     t_e2e = timed(e2e_run, 1)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sampler is not None:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
