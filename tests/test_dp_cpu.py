@@ -100,6 +100,25 @@ def _worker(rank, world, port, out):
         with config.override(global_nce=False):
             z = torch.randn(3, 5, requires_grad=True)
             assert ops.gather_rows(z) is z
+        # the drop-in U-Net under the reducer, kernels replaced by a no-op recorder (host plumbing only): every parameter's gradient
+        # must end up aliasing its bucket after backward -- including the fused last-unit + head op, whose Function hands back the
+        # gradients of final_conv and of the last block at once -- and a second step must reuse the same buckets
+        from src.models.networks.UNet import UNet
+        trace = []
+        ops.call = lambda name, *a: trace.append(name)
+        ops._stream = lambda: 0
+        ops._require_cuda = lambda t, what: None
+        unet = UNet(depth=3, use_3D=True, top_filter=16, midchannels_factor=2, p_dropout=0.0).train()
+        red = dp.install(unet, bucket_bytes=32 << 10)
+        assert len(red.buckets) >= 3
+        for _ in range(2):
+            unet.zero_grad()
+            unet(torch.rand(1, 1, 8, 16, 16)).sum().backward()
+            for b in red.buckets:
+                assert b.pending == len(b.params) and b.work is None
+                lo, hi = b.flat.data_ptr(), b.flat.data_ptr() + b.flat.numel() * 4
+                assert all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in b.params)
+        assert 'ich_bn_head_bwd' in trace
         out.put((rank, 'ok'))
     except Exception as e:  # noqa: BLE001
         import traceback
