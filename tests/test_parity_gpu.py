@@ -892,6 +892,50 @@ def test_training_loop_checkpoint_and_frozen_transfer(golden):
         assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in tgt.up_block.parameters())
 
 
+FULL_SIZE = [  # BASELINE cfg-3 layer shapes (per-GPU batch 8): N, D, H, W, Cin, Cout
+    (8, 64, 128, 128, 32, 32),     # u2.c2: plane-streaming kernel, 268 M output elements; wgrad kw-fold (N = 96)
+    (8, 32, 64, 64, 128, 64),      # u1.c1: slab kernel; wgrad kw-fold + kh-split (N = 192, 128-byte dy rows)
+    (8, 64, 128, 128, 1, 16),      # d0.c1: first layer, tcgen05 im2col kernels (forward + weight gradient)
+    (4, 64, 128, 128, 64, 32),     # u2.c1 (half batch): two Cin blocks in the kw-fold wgrad, KC = 4 in the streaming kernel
+    (8, 16, 32, 32, 64, 128),      # d2.c2: wgrad kh-split with N = 128 (128-byte dy rows, two blocks)
+]
+
+
+@pytest.mark.parametrize('case', FULL_SIZE)
+def test_full_size_layer_against_torch_fp32_conv(case):
+    """Full-size parity (BASELINE cfg-3 layer shapes): the tcgen05 forward / data-gradient / weight-gradient kernels against
+    torch's fp32 conv3d on the GPU (cuDNN with TF32 off) used purely as the CHECKER, on identical bf16-representable operands."""
+    n, d, h, w, cin, cout = case
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator(device=DEV).manual_seed(1)
+        x = torch.randn(n, d, h, w, cin, device=DEV, generator=g).bfloat16()
+        dy = torch.randn(n, d, h, w, cout, device=DEV, generator=g).bfloat16()
+        wt = (torch.randn(cout, cin, 3, 3, 3, device=DEV, generator=g) * 0.05).bfloat16().float()
+        with config.override(precision='bf16', tensor_cores=True):
+            y = ops.conv_forward(x, wt, None)
+            dx = ops.conv_dgrad(dy, wt) if cin > 1 else None      # the first layer's data gradient is never needed (ICH_B200_INPUT_GRAD=0)
+            dw = ops.conv_wgrad(x, dy, wt)
+        xr = x.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
+        wr = wt.clone().requires_grad_(True)
+        yr = F.conv3d(xr, wr, None, padding=1)
+        yr.backward(dy.float().permute(0, 4, 1, 2, 3).contiguous())
+
+        def relg(a, b):
+            return ((a.float() - b.float()).norm() / b.float().norm()).item()
+        assert relg(y.permute(0, 4, 1, 2, 3), yr.detach()) < 4e-3
+        if dx is not None:
+            assert relg(dx.permute(0, 4, 1, 2, 3), xr.grad) < 4e-3
+        assert relg(dw, wr.grad) < 2e-3
+        # size-independent property: the conv is linear -> conv(2x) == 2 conv(x) exactly in bf16 (power-of-two scaling)
+        with config.override(precision='bf16', tensor_cores=True):
+            y2 = ops.conv_forward(x * 2, wt, None)
+        assert torch.equal(y2.float(), y.float() * 2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
 _CFG1 = {}
 
 
@@ -945,47 +989,3 @@ def test_cfg1_full_size_forward_and_loss(prec):
     sd_after = net.state_dict()
     for k, v in c['new_stats'].items():                                # BatchNorm running statistics after one training step
         assert rel(sd_after[k].float(), v.float()) < tol, k
-
-
-FULL_SIZE = [  # BASELINE cfg-3 layer shapes (per-GPU batch 8): N, D, H, W, Cin, Cout
-    (8, 64, 128, 128, 32, 32),     # u2.c2: plane-streaming kernel, 268 M output elements; wgrad kw-fold (N = 96)
-    (8, 32, 64, 64, 128, 64),      # u1.c1: slab kernel; wgrad kw-fold + kh-split (N = 192, 128-byte dy rows)
-    (8, 64, 128, 128, 1, 16),      # d0.c1: first layer, tcgen05 im2col kernels (forward + weight gradient)
-    (4, 64, 128, 128, 64, 32),     # u2.c1 (half batch): two Cin blocks in the kw-fold wgrad, KC = 4 in the streaming kernel
-    (8, 16, 32, 32, 64, 128),      # d2.c2: wgrad kh-split with N = 128 (128-byte dy rows, two blocks)
-]
-
-
-@pytest.mark.parametrize('case', FULL_SIZE)
-def test_full_size_layer_against_torch_fp32_conv(case):
-    """Full-size parity (BASELINE cfg-3 layer shapes): the tcgen05 forward / data-gradient / weight-gradient kernels against
-    torch's fp32 conv3d on the GPU (cuDNN with TF32 off) used purely as the CHECKER, on identical bf16-representable operands."""
-    n, d, h, w, cin, cout = case
-    old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        g = torch.Generator(device=DEV).manual_seed(1)
-        x = torch.randn(n, d, h, w, cin, device=DEV, generator=g).bfloat16()
-        dy = torch.randn(n, d, h, w, cout, device=DEV, generator=g).bfloat16()
-        wt = (torch.randn(cout, cin, 3, 3, 3, device=DEV, generator=g) * 0.05).bfloat16().float()
-        with config.override(precision='bf16', tensor_cores=True):
-            y = ops.conv_forward(x, wt, None)
-            dx = ops.conv_dgrad(dy, wt) if cin > 1 else None      # the first layer's data gradient is never needed (ICH_B200_INPUT_GRAD=0)
-            dw = ops.conv_wgrad(x, dy, wt)
-        xr = x.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_(True)
-        wr = wt.clone().requires_grad_(True)
-        yr = F.conv3d(xr, wr, None, padding=1)
-        yr.backward(dy.float().permute(0, 4, 1, 2, 3).contiguous())
-
-        def relg(a, b):
-            return ((a.float() - b.float()).norm() / b.float().norm()).item()
-        assert relg(y.permute(0, 4, 1, 2, 3), yr.detach()) < 4e-3
-        if dx is not None:
-            assert relg(dx.permute(0, 4, 1, 2, 3), xr.grad) < 4e-3
-        assert relg(dw, wr.grad) < 2e-3
-        # size-independent property: the conv is linear -> conv(2x) == 2 conv(x) exactly in bf16 (power-of-two scaling)
-        with config.override(precision='bf16', tensor_cores=True):
-            y2 = ops.conv_forward(x * 2, wt, None)
-        assert torch.equal(y2.float(), y.float() * 2)
-    finally:
-        torch.backends.cudnn.allow_tf32 = old
