@@ -74,6 +74,10 @@ class ConvBlock(nn.Module):
         if conv.padding[0] * 2 + 1 != conv.kernel_size[0]:
             _not_built(f'kernel_size={conv.kernel_size} with padding={conv.padding}')
         training = self.training or not bn.track_running_stats
+        if not training and not concat_c and _cfg.get('fold_eval_bn') and not torch.is_grad_enabled():
+            # inference: BatchNorm folded into the conv (one launch, bias + ReLU epilogue)
+            w_eff, b_eff = ops.folded_eval_unit(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+            return ops.conv_forward(x, w_eff, b_eff, relu=True)
         z = ops.ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, True, concat_c,
                                  drop_p)
         if concat_c:

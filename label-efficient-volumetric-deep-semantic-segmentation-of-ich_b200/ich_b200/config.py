@@ -23,6 +23,10 @@ _state = {
     # BN+ReLU output of that unit is never materialised and its gradient is rebuilt inside the BatchNorm-backward passes
     # (measured at cfg-3: 15.57 -> 15.19 ms/step, end to end 16.25 -> 15.99; 0 = separate BN-apply / head kernels)
     'fuse_head': os.environ.get('ICH_B200_FUSE_HEAD', '1') == '1',
+    # inference (eval mode under torch.no_grad): fold BatchNorm into the conv weights, one conv launch with a bias + ReLU epilogue per
+    # unit instead of conv + bn_finalize + BN-apply (ops.folded_eval_unit).  Host logic over kernels that are already parity-tested;
+    # not yet timed on a GPU -> off by default
+    'fold_eval_bn': os.environ.get('ICH_B200_FOLD_EVAL_BN', '0') == '1',
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

@@ -412,6 +412,30 @@ def _conv_bn_stats(x, weight, bias, gamma, beta, running_mean, running_var, trai
     return y, stats, comm is not None
 
 
+def folded_eval_unit(weight, bias, gamma, beta, running_mean, running_var):
+    """Inference only (eval mode, no autograd): BatchNorm folded into the conv, so that Conv -> BN -> ReLU (reference UNet.py:173-174)
+    is ONE conv launch with a bias + ReLU epilogue -- no bn_finalize, no BN-apply pass, no pre-BN tensor.
+    w' = w * scale[co], b' = beta + (conv_bias - running_mean) * scale with scale = gamma / sqrt(running_var + eps).
+    Derived cache on the weight tensor, keyed on the versions / storage of everything it depends on."""
+    deps = (weight, bias, gamma, beta, running_mean, running_var)
+    key = tuple((t._version, t.data_ptr()) for t in deps if t is not None)
+    cache = getattr(weight, '_ich_folded', None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            scale = torch.rsqrt(running_var.float() + BN_EPS)
+            if gamma is not None:
+                scale = scale * gamma.float()
+            shift = -running_mean.float() * scale
+            if bias is not None:
+                shift = shift + bias.float() * scale
+            if beta is not None:
+                shift = shift + beta.float()
+            w_eff = (weight.detach().float() * scale.view(-1, *([1] * (weight.dim() - 1)))).contiguous()
+        cache = (key, w_eff, shift.contiguous())
+        weight._ich_folded = cache
+    return cache[1], cache[2]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Conv -> BatchNorm -> ReLU  (one unit of ConvBlock.forward, models/networks/UNet.py:173-174)
 # ---------------------------------------------------------------------------------------------------------------

@@ -129,6 +129,46 @@ def test_unet2d_variants_plumbing(dry, kw):
         assert net(x)[0].shape == out.shape
 
 
+def test_folded_eval_bn_plumbing(dry):
+    """ICH_B200_FOLD_EVAL_BN: under eval + no_grad every unit but the fused last one is ONE conv launch (BatchNorm folded into the
+    weights, bias + ReLU epilogue); training mode, eval with autograd and the default configuration keep the BatchNorm kernels.
+    The folded weights are a cache keyed on the versions of the tensors they derive from."""
+    from src.models.networks.UNet import UNet
+    x = torch.rand(1, 1, 8, 16, 16)
+    net = UNet(depth=3, use_3D=True, top_filter=16, midchannels_factor=2, p_dropout=0.0).eval()
+    with config.override(fold_eval_bn=True):
+        with torch.no_grad():
+            assert net(x).shape == x.shape
+        t = dry.trace
+        assert t.count('ich_bn_finalize') == 1 and t.count('ich_bn_head_fwd') == 1 and 'ich_affine_act' not in t
+        conv = net.down_block[1].conv1
+        w1, b1 = ops.folded_eval_unit(conv.weight, conv.bias, net.down_block[1].bn1.weight, net.down_block[1].bn1.bias,
+                                      net.down_block[1].bn1.running_mean, net.down_block[1].bn1.running_var)
+        bn = net.down_block[1].bn1
+        want = conv.weight.detach() * (bn.weight / torch.sqrt(bn.running_var + 1e-5)).view(-1, 1, 1, 1, 1).detach()
+        assert torch.allclose(w1, want, rtol=1e-6, atol=1e-8)
+        assert torch.allclose(b1, (bn.bias + (conv.bias - bn.running_mean) * bn.weight / torch.sqrt(bn.running_var + 1e-5)).detach(), atol=1e-7)
+        w2, _ = ops.folded_eval_unit(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        assert w2 is w1                                             # cached
+        with torch.no_grad():
+            bn.running_var.mul_(2.0)                                # e.g. load_state_dict copying in place
+        w3, _ = ops.folded_eval_unit(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        assert w3 is not w1 and not torch.allclose(w3, w1)
+        dry.trace.clear()
+        net(x).sum().backward()                                     # eval WITH autograd: unfolded path
+        assert dry.trace.count('ich_bn_finalize') == 10
+        net.train()
+        dry.trace.clear()
+        with torch.no_grad():
+            net(x)
+        assert dry.trace.count('ich_bn_finalize') == 10
+    net.eval()
+    dry.trace.clear()
+    with torch.no_grad():
+        net(x)
+    assert dry.trace.count('ich_bn_finalize') == 10                 # default: off
+
+
 def test_contrastive_nets_plumbing(dry):
     from src.models.networks.UNet import UNet_Encoder, Partial_UNet
     from src.models.optim.LossFunctions import InfoNCELoss, LocalInfoNCELoss

@@ -989,3 +989,24 @@ def test_cfg1_full_size_forward_and_loss(prec):
     sd_after = net.state_dict()
     for k, v in c['new_stats'].items():                                # BatchNorm running statistics after one training step
         assert rel(sd_after[k].float(), v.float()) < tol, k
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_folded_eval_batchnorm_inference(golden, prec):
+    """ICH_B200_FOLD_EVAL_BN (opt-in): eval-mode inference with BatchNorm folded into the conv weights (one conv launch with a bias + ReLU
+    epilogue per unit) against the reference's eval output of the golden run, and against the unfolded engine path."""
+    from src.models.networks.UNet import UNet
+    fx = golden('unet3d_combo.pt')
+    outs = {}
+    for fold in (False, True):
+        with config.override(precision=prec, fold_eval_bn=fold):
+            net = UNet(**fx['kwargs'])
+            net.load_state_dict(fx['state_dict_after'])
+            net = net.to(DEV).eval()
+            with torch.no_grad():
+                outs[fold] = net(fx['x'].to(DEV)).cpu()
+    tol = TOL[prec]
+    assert rel(outs[True], fx['out_eval']) < tol and rel(outs[True], outs[False]) < tol
+    if prec == 'fp32':
+        near = (fx['out_eval'] - 0.5).abs() < 1e-5
+        assert torch.equal((outs[True] >= 0.5)[~near], (fx['out_eval'] >= 0.5)[~near])
