@@ -27,6 +27,9 @@ _state = {
     # unit instead of conv + bn_finalize + BN-apply (ops.folded_eval_unit).  Host logic over kernels that are already parity-tested;
     # not yet timed on a GPU -> off by default
     'fold_eval_bn': os.environ.get('ICH_B200_FOLD_EVAL_BN', '0') == '1',
+    # re-derive the kernel-layout weight packs from a global optimizer post-step hook (hidden behind the GPU's backlog) instead of at
+    # the start of the next forward pass (0 = only there)
+    'refresh_after_step': os.environ.get('ICH_B200_REFRESH_AFTER_STEP', '1') == '1',
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

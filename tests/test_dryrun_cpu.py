@@ -169,6 +169,41 @@ def test_folded_eval_bn_plumbing(dry):
     assert dry.trace.count('ich_bn_finalize') == 10                 # default: off
 
 
+def test_weight_packs_refreshed_from_the_optimizer_hook(dry, monkeypatch):
+    """The packs the optimizer step invalidated are re-derived in ONE batched launch from the global optimizer post-step hook; the
+    refresh at the start of the next forward pass then has nothing to do.  ICH_B200_REFRESH_AFTER_STEP=0 restores refresh-at-forward."""
+    from src.models.networks.UNet import UNet
+    from src.models.optim.LossFunctions import ComboLoss
+    monkeypatch.setattr(ops, '_REFRESH_ANY_DEVICE', True)
+    x = torch.rand(1, 1, 8, 16, 16)
+    net = UNet(depth=3, use_3D=True, top_filter=16, midchannels_factor=2, p_dropout=0.0).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    ComboLoss()(net(x), torch.zeros_like(x)).backward()
+    n_single = dry.trace.count('ich_permute5')                  # first use: one derivation per pack
+    assert n_single > 10 and 'ich_permute5_batch' not in dry.trace
+    dry.trace.clear()
+    opt.step()
+    assert dry.trace == ['ich_permute5_batch']                  # from the hook
+    assert ops.refresh_packs() == 0                             # nothing left for the forward pass
+    dry.trace.clear()
+    ComboLoss()(net(x), torch.zeros_like(x)).backward()
+    assert 'ich_permute5' not in dry.trace and 'ich_permute5_batch' not in dry.trace
+    with config.override(refresh_after_step=False):
+        dry.trace.clear()
+        opt.step()
+        assert dry.trace == []
+        net(x)
+        assert dry.trace[0] == 'ich_layout_nc_to_nl' or dry.trace[0] == 'ich_permute5_batch'
+        assert dry.trace.count('ich_permute5_batch') == 1 and 'ich_permute5' not in dry.trace
+    # an unrelated optimizer in the same process does not disturb anything
+    lin = torch.nn.Linear(2, 2)
+    o2 = torch.optim.SGD(lin.parameters(), lr=0.1)
+    lin(torch.rand(1, 2)).sum().backward()
+    dry.trace.clear()
+    o2.step()
+    assert dry.trace == []
+
+
 def test_contrastive_nets_plumbing(dry):
     from src.models.networks.UNet import UNet_Encoder, Partial_UNet
     from src.models.optim.LossFunctions import InfoNCELoss, LocalInfoNCELoss
