@@ -1,6 +1,7 @@
 """torch.autograd.Function wrappers over the C-ABI kernels. They own save-for-backward and workspaces (torch tensors);
 the library never allocates.  Internal activations are channel-last [N, D, H, W, C] tensors (2-D nets: D = 1) in the
 engine dtype (bf16 or fp32, ich_b200.config).  Call sites cite the reference lines they replace."""
+import contextlib
 import weakref
 
 import torch
@@ -122,8 +123,10 @@ _REFRESH_ANY_DEVICE = False     # tests: let refresh_packs() batch CPU tensors t
 
 
 def refresh_packs():
-    """Called at the start of a forward pass: every pack that was in use before the last optimizer step is re-derived now, all of
-    them in one kernel launch (ich_permute5_batch) instead of one launch per layer and kind spread over forward and backward."""
+    """Every pack that was in use before the last in-place parameter update is re-derived now, all of them in one kernel launch
+    (ich_permute5_batch) instead of one launch per layer and kind spread over forward and backward.  Called right after every
+    optimizer step (global post-step hook below) and again at the start of a forward pass (normally a no-op then).  Returns the
+    number of packs re-derived."""
     import ctypes
     jobs = []
     dev = None
@@ -158,7 +161,6 @@ def refresh_packs():
     dims = (ctypes.c_int * (5 * n))(*[d for j in jobs for d in j[3]])
     perm = (ctypes.c_int * (5 * n))(*[q for j in jobs for q in j[4]])
     flip = (ctypes.c_int * n)(*[j[5] for j in jobs])
-    import contextlib
     with (torch.cuda.device(dev) if dev.type == 'cuda' else contextlib.nullcontext()):
         call('ich_permute5_batch', n, ctypes.cast(src, ctypes.c_void_p), ctypes.cast(dst, ctypes.c_void_p), ctypes.cast(dt, ctypes.c_void_p),
              ctypes.cast(dims, ctypes.c_void_p), ctypes.cast(perm, ctypes.c_void_p), ctypes.cast(flip, ctypes.c_void_p), _stream())
