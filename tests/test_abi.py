@@ -93,3 +93,18 @@ def test_no_cpu_fallback(golden):
         ComboLoss()(torch.rand(1, 1, 4, 4), torch.rand(1, 1, 4, 4))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         InfoNCELoss(set_size=2, device='cpu')(torch.rand(2, 4), torch.rand(2, 4))
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package may import it (a product path that routes through the oracle or any
+    CPU restatement would void every parity claim)."""
+    import re
+    pkg = os.path.dirname(os.path.dirname(os.path.abspath(_lib.__file__)))
+    offenders = []
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, f), errors='ignore').read()
+                if re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M) or 'oracle/' in text:
+                    offenders.append(os.path.join(root, f))
+    assert not offenders, offenders
