@@ -49,6 +49,11 @@ def _flush_nbt():
         _PENDING_NBT.clear()
 
 
+def _begin_forward():
+    """Start of a top-level forward: counters queued by a forward pass that raised half-way are dropped, not applied to this pass."""
+    _PENDING_NBT.clear()
+
+
 def _not_built(what):
     raise NotImplementedError(f'ich_b200: {what} is not part of the B200 hot path yet (SURVEY section 8f); '
                               f'refusing to fall back silently')
@@ -109,6 +114,7 @@ class ConvBlock(nn.Module):
         return out
 
     def forward(self, input):
+        _begin_forward()
         was_4d = input.dim() == 4
         out = ops.from_channels_last(self.forward_cl(ops.to_channels_last(input)), was_4d)
         _flush_nbt()
@@ -229,9 +235,23 @@ class UNet(_UNetBase):
         super(UNet, self).__init__()
         p_dropout_list = _dropout_list(p_dropout, depth)
         self.return_bottleneck = False
-        down, bottleneck = self._build_encoder(depth, use_3D, in_channels, top_filter, midchannels_factor, p_dropout_list)
+        # module lists registered as down_block, up_samp, up_block (state-dict key order) and FILLED in the reference's interleaved order
+        # down_block[i], up_block[i], up_samp[i] (UNet.py:66-76): the parameter initialisation draws from the global RNG in construction
+        # order, so the same torch.manual_seed gives the same initial weights as the reference
+        down, bottleneck = _filters(in_channels, top_filter, depth)
         up_filters = [(top_filter * 2 ** d, top_filter * 2 ** (d - 1)) for d in range(depth - 1, 0, -1)]
-        self._build_decoder(up_filters, use_3D, bilinear)
+        self.down_block = nn.ModuleList()
+        self.up_samp = nn.ModuleList()
+        self.up_block = nn.ModuleList()
+        for down_ch, up_ch, p in zip(down, up_filters, p_dropout_list[:-1]):
+            self.down_block.append(ConvBlock(down_ch[0], down_ch[1], mid_channels=down_ch[1] // midchannels_factor, use_3D=use_3D, p_dropout=p))
+            if bilinear:
+                self.up_block.append(ConvBlock(int(1.5 * up_ch[0]), up_ch[1], mid_channels=up_ch[1], use_3D=use_3D))
+                self.up_samp.append(nn.Upsample(scale_factor=2, mode='trilinear' if use_3D else 'bilinear', align_corners=True))
+            else:
+                self.up_block.append(ConvBlock(up_ch[0], up_ch[1], mid_channels=up_ch[1], use_3D=use_3D))
+                convT = nn.ConvTranspose3d if use_3D else nn.ConvTranspose2d
+                self.up_samp.append(convT(up_ch[0], up_ch[1], kernel_size=2, stride=2))
         self._build_bottleneck(bottleneck, use_3D, midchannels_factor, p_dropout_list[-1])
         self.final_conv = nn.Conv3d(top_filter, out_channels, kernel_size=1) if use_3D else nn.Conv2d(top_filter, out_channels, kernel_size=1)
         if use_final_activation:
@@ -240,6 +260,7 @@ class UNet(_UNetBase):
             self.final_activation = nn.Identity()
 
     def forward(self, input):
+        _begin_forward()
         was_4d = input.dim() == 4
         x = ops.to_channels_last(input)
         x, res = self._encode(x)
@@ -273,6 +294,7 @@ class UNet_Encoder(_UNetBase):
         self.mlp_head = MLPHead(Neurons_layer=[bottleneck[1]] + MLP_head)
 
     def forward(self, input):
+        _begin_forward()
         was_4d = input.dim() == 4
         x, _ = self._encode(ops.to_channels_last(input))
         _flush_nbt()
@@ -299,6 +321,7 @@ class Partial_UNet(_UNetBase):
         self.final_conv = ConvHead(channel_layer=[up_filters[-1][1]] + head_channel, use_3D=use_3D)
 
     def forward(self, input):
+        _begin_forward()
         was_4d = input.dim() == 4
         x, res = self._encode(ops.to_channels_last(input))
         x_bottleneck = x

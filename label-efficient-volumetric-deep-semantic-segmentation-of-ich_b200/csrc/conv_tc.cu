@@ -447,7 +447,9 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(w) failed with %d", what, (int)r);
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is a per-DEVICE setting
+  int attr_dev = 0; cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_done[attr_dev & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
@@ -843,7 +845,9 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy) failed with %d", what, (int)r);
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is a per-DEVICE setting
+  int attr_dev = 0; cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_done[attr_dev & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));

@@ -490,7 +490,9 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(w) failed with %d", what, (int)r);
   }
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is a per-DEVICE setting
+  int attr_dev = 0; cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_done[attr_dev & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_stream_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_stream_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));

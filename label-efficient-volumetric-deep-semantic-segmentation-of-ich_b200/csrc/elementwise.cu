@@ -1168,7 +1168,9 @@ static void bn_act_bwd_launch(const void* dz, int dz_ld, const void* y, int y_ld
   unsigned blocks = (unsigned)((M + rows_per_block - 1) / rows_per_block);
   size_t shbytes = sizeof(float) * 2 * C;
   bool vec = vec_ok<T>(dz, dz_ld, C) && vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C);
-  if (vec && rows_fast_ok(C, Vec<T>::N)) {
+  // the rows kernel keeps 8 per-warp copies of the [2][C] partial sums in shared memory: stay under the 48 KB default limit
+  // (C = 1024 -- the bottleneck of the default depth-5 / 64-filter constructor -- takes the generic path below)
+  if (vec && rows_fast_ok(C, Vec<T>::N) && 8 * shbytes <= 48 * 1024) {
     const int grid = rows_grid(M, C, Vec<T>::N);
     if (phases & 1) bn_bwd_reduce_rows_kernel<T, DROPV><<<grid, 256, 8 * shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, M, C, relu, sums, drop);
     if (phases & 2) bn_bwd_apply_rows_kernel<T, DROPV><<<grid, 256, shbytes, s>>>((const T*)dz, dz_ld, (const T*)y, y_ld, scale, shift, mean, invstd, sums, (T*)dy, dy_ld, M, C, relu, training, dgamma, dbeta, drop, count);

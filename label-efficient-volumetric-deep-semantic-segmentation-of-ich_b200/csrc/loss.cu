@@ -568,7 +568,9 @@ int ich_infonce_fwd(const float* P, int B, int R, int E, float tau, float* Pn, f
   int rows = B * R;
   rownorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(P, Pn, invn, rows, E, 1e-8f);
   size_t sh = sizeof(float) * (E + 64);
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is a per-DEVICE setting
+  int attr_dev = 0; cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_done[attr_dev & 63];
   if (!attr_set) { cudaFuncSetAttribute(infonce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
   infonce_fwd_kernel<<<dim3(R, B), 256, sh, s>>>(Pn, R, E, 1.f / tau, lse, rowloss, loss, counter, rows);
   return ich_check_launch("ich_infonce_fwd");
@@ -579,7 +581,9 @@ int ich_infonce_bwd(const float* Pn, const float* invn, const float* lse, int B,
   cudaStream_t s = (cudaStream_t)stream;
   size_t sh = sizeof(float) * (E + R + 32);
   ICH_REQUIRE(sh <= 200 * 1024, "ich_infonce_bwd: E + R too large (%d, %d)", E, R);
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // cudaFuncSetAttribute is a per-DEVICE setting
+  int attr_dev = 0; cudaGetDevice(&attr_dev);
+  bool& attr_set = attr_done[attr_dev & 63];
   if (!attr_set) { cudaFuncSetAttribute(infonce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
   infonce_bwd_kernel<<<dim3(R, B), 256, sh, s>>>(Pn, invn, lse, R, E, 1.f / tau, gout, 1.f / (float)(B * R), dP);
   return ich_check_launch("ich_infonce_bwd");

@@ -23,6 +23,9 @@ _CTYPE = {'int': ctypes.c_int, 'long long': ctypes.c_longlong, 'float': ctypes.c
           'unsigned int': ctypes.c_uint}
 
 
+ARG_NAMES = {}       # entry point -> argument names as declared in the header (profiling: algorithmic bytes per launch)
+
+
 def parse_header(path=HEADER):
     """Return {name: (restype, [argtypes])} for every prototype in the header."""
     text = open(path).read()
@@ -30,16 +33,18 @@ def parse_header(path=HEADER):
     protos = {}
     for m in re.finditer(r'(const char\*|int)\s+(ich_\w+)\s*\(([^)]*)\)\s*;', text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
-        argtypes = []
+        argtypes, names = [], []
         if args and args != 'void':
             for a in args.split(','):
                 a = a.strip()
+                names.append(re.search(r'(\w+)$', a).group(1))
                 if '*' in a:
                     argtypes.append(ctypes.c_void_p)
                 else:
                     typ = re.sub(r'\s+\w+$', '', a).replace('const ', '').strip()
                     argtypes.append(_CTYPE[typ])
         protos[name] = (ctypes.c_char_p if 'char' in ret else ctypes.c_int, argtypes)
+        ARG_NAMES[name] = names
     return protos
 
 
@@ -111,9 +116,23 @@ def launches():
     return sum(LAUNCHES.values())
 
 
+# bench.py sets PROFILE = [] to collect (entry point, {arg name: value}, start event, end event) for every launch (CUDA events on the
+# launching stream); None = off (the normal state: no events, no overhead)
+PROFILE = None
+TAG = None            # set by ops._Timed: 'fwd' / 'dgrad' / 'wgrad' of the conv launch being made
+
+
 def call(name, *args):
     l = lib()
     LAUNCHES[name] = LAUNCHES.get(name, 0) + KERNELS_PER_CALL.get(name, 1)
-    rc = getattr(l, name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(l, name)(*args)
+        e1.record()
+        PROFILE.append((name, dict(zip(ARG_NAMES.get(name, ()), args)), TAG, e0, e1))
+    else:
+        rc = getattr(l, name)(*args)
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {l.ich_last_error().decode()}')

@@ -8,6 +8,7 @@ import torch
 from torch.autograd import Function
 
 from . import config
+from . import _lib as _libmod
 from ._lib import call
 
 BN_EPS = 1e-5
@@ -119,6 +120,23 @@ def _pack(param, kind):
     return cache['bufs'][kind]
 
 
+def invalidate_packs(module_or_params=None):
+    """Drop the derived weight packs (and folded inference weights) of a module / an iterable of parameters / everything (None).
+    The caches are keyed on the parameter's autograd version counter, which `load_state_dict` and torch optimizers bump; in-place
+    writes through `param.data` (`p.data.copy_()`, EMA updates, manual weight surgery) do NOT bump it -- call this after such writes."""
+    if module_or_params is None:
+        params = list(_PACKED_PARAMS)
+    elif hasattr(module_or_params, 'parameters'):
+        params = list(module_or_params.parameters())
+    else:
+        params = list(module_or_params)
+    for p in params:
+        for attr in ('_ich_packs', '_ich_folded'):
+            if hasattr(p, attr):
+                delattr(p, attr)
+        _PACKED_PARAMS.discard(p)
+
+
 _REFRESH_ANY_DEVICE = False     # tests: let refresh_packs() batch CPU tensors too (the launch itself is mocked there)
 
 
@@ -227,25 +245,19 @@ def _sync_bn_comm():
     return dist.get_world_size(), (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
 
 
-# bench.py sets PROFILE = [] to collect (kind, flops, start_event, end_event) per conv kernel launch
-PROFILE = None
-
-
 class _Timed:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    """Tags the conv launches made inside the block with their direction ('fwd' / 'dgrad' / 'wgrad') for the per-launch profile that
+    bench.py collects through `_lib.PROFILE` (no effect otherwise)."""
+
+    def __init__(self, kind, flops=0.0):
+        self.kind = kind
 
     def __enter__(self):
-        if PROFILE is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e1 = torch.cuda.Event(enable_timing=True)
-            self.e0.record()
+        _libmod.TAG = self.kind
         return self
 
     def __exit__(self, *a):
-        if PROFILE is not None:
-            self.e1.record()
-            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+        _libmod.TAG = None
         return False
 
 

@@ -53,9 +53,10 @@ def info_nce_loss(z1, z2, tau=0.5):
     n = z1.shape[0]
     p = torch.cat((z1, z2), dim=0)
     s = _cos_sim_matrix(p) / tau
-    eye = torch.eye(2 * n, dtype=torch.bool)
+    eye = torch.eye(2 * n, dtype=torch.bool, device=s.device)
     lse = torch.logsumexp(s.masked_fill(eye, float('-inf')), dim=1)
-    pos = s[torch.arange(2 * n), (torch.arange(2 * n) + n) % (2 * n)]
+    ar = torch.arange(2 * n, device=s.device)
+    pos = s[ar, (ar + n) % (2 * n)]
     return (lse - pos).mean()
 
 
@@ -88,9 +89,9 @@ def local_info_nce_loss(f1, f2, tau=0.5, K=3, n_region=13):
     p = torch.cat((gather(f1), gather(f2)), dim=1)                            # B x 2A x K*K*C
     s = _cos_sim_matrix(p) / tau
     a2 = 2 * n_region
-    eye = torch.eye(a2, dtype=torch.bool)
+    eye = torch.eye(a2, dtype=torch.bool, device=s.device)
     lse = torch.logsumexp(s.masked_fill(eye, float('-inf')), dim=2)
-    ar = torch.arange(a2)
+    ar = torch.arange(a2, device=s.device)
     pos = s[:, ar, (ar + n_region) % a2]
     return (lse - pos).mean()
 

@@ -2,11 +2,14 @@
 the reference's API surface (constructor validation, attribute tree, state-dict keys) and refuse to run without CUDA."""
 import ctypes
 import os
+import sys
 
 import pytest
 import torch
 
 from ich_b200 import _lib
+
+PKG = _lib.PKG_ROOT
 
 
 def test_library_exports_every_declared_symbol():
@@ -108,3 +111,26 @@ def test_product_path_never_imports_the_oracle():
                 if re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M) or 'oracle/' in text:
                     offenders.append(os.path.join(root, f))
     assert not offenders, offenders
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/code'), reason='needs the reference tree (present in the build container only)')
+def test_same_seed_same_initial_weights_as_reference():
+    """The drop-in builds its sub-modules in the reference's construction order (UNet.py:66-76 interleaves down_block[i], up_block[i],
+    up_samp[i]), so `torch.manual_seed(s); UNet(...)` draws the same initial parameters as the reference (seeded-run comparability,
+    UNet2D_scripts.py:53-60).  Checked in a child process: both package trees are called `src`."""
+    import subprocess
+    code = '''
+import sys, torch
+sys.dont_write_bytecode = True
+sys.path.insert(0, sys.argv[1])
+from src.models.networks.UNet import UNet, UNet_Encoder, Partial_UNet
+cases = [(UNet, dict(depth=4, use_3D=True, top_filter=8, p_dropout=0.0)), (UNet, dict(depth=3, bilinear=True, top_filter=8)),
+         (UNet_Encoder, dict(depth=3, top_filter=8, MLP_head=[16, 8])), (Partial_UNet, dict(depth=4, n_decoder=2, top_filter=8, head_channel=[8, 4]))]
+for cls, kw in cases:
+    torch.manual_seed(3)
+    sd = cls(**kw).state_dict()
+    print(cls.__name__, len(sd), ' '.join(f'{v.double().sum().item():.10e}' for v in sd.values()))
+'''
+    outs = [subprocess.run([sys.executable, '-c', code, path], capture_output=True, text=True, check=True).stdout
+            for path in ('/root/reference/code', os.path.join(PKG, 'code'))]
+    assert outs[0] == outs[1] and outs[0].count('\n') == 4
