@@ -375,8 +375,7 @@ def main():
     step_fn = job.step
     if args.graph and args.impl == 'b200' and job.opt is not None:
         from ich_b200.graph import GraphedStep
-        graphed = GraphedStep(job.net, job.lossf if job.kind == 'seg' else None, job.opt, step=job.step)
-        step_fn = graphed
+        step_fn = GraphedStep(job.step, job.opt, warmup=2)       # calls 1-2 eager, call 3 (still warm-up, >= 3 enforced above) captures
 
     def barrier():
         if world > 1:

@@ -187,6 +187,32 @@ int ich_region_scatter(const float* dP, const int* corners, float* df, int bs, i
 /* ---- batch_binary_confusion_matrix (utils/tensor_utils.py:12-36) with the >= 0.5 threshold of models/optim/UNet2D.py:220 -- */
 int ich_confusion(const float* pred, const float* target, int B, long long S, float thr, double* out, void* stream);
 
+/* ---- input staging: raw CT -> window -> clip -> engine dtype in ONE pass.  Replaces the host-side
+ *      window_ct (utils/ct_utils.py:13-36), the `input.to(device).float()` of models/optim/UNet2D.py:137-138 / :297 and the layout hop (a
+ *      one-channel volume is already channel-last).  src_dtype: 0 fp32, 1 int16, 2 uint16, 3 uint8 (Hounsfield units or raw intensities). */
+int ich_stage_ct(const void* src, int src_dtype, void* dst, int dtype, long long M, float win_min, float win_max, float out_lo, float out_hi,
+                 void* stream);
+
+/* ---- sliding-window volume inference on the device (models/optim/UNet2D.py:272-314 as a 3-D window driver):
+ *      window extraction from a one-channel volume [D][H][W]; stitching of the fp32 predictions [n_win][wd][wh][ww] with the
+ *      `pred >= 0.5` mask of UNet2D.py:220,303.  starts = device int [n_win][3] = (d0, h0, w0).  mode 0: windows do not overlap, acc
+ *      (optional) and mask (optional, uint8) are written directly; mode 1: acc / cnt accumulate (fp32 atomics), then
+ *      ich_blend_threshold divides and thresholds (mean blending of the overlaps). */
+int ich_window_gather(const void* vol, int dtype, int D, int H, int W, const int* starts, int n_win, int wd, int wh, int ww, void* out, void* stream);
+int ich_window_scatter(const float* pred, int D, int H, int W, const int* starts, int n_win, int wd, int wh, int ww, int mode, float thr,
+                       float* acc, float* cnt, unsigned char* mask, void* stream);
+int ich_blend_threshold(float* acc, const float* cnt, long long M, float thr, unsigned char* mask, void* stream);
+
+/* ---- MLPHead (models/networks/UNet.py:179-209): Linear (+ReLU) on a [B, K] fp32 matrix, w = [N][K] (nn.Linear layout).
+ *      bwd: `out` = the forward output (ReLU mask), any of dx / dw / db may be NULL (db is produced with dw). */
+int ich_linear_fwd(const float* x, const float* w, const float* bias, float* out, int B, int K, int N, int relu, void* stream);
+int ich_linear_bwd(const float* dout, const float* out, const float* x, const float* w, float* dx, float* dw, float* db, int B, int K, int N,
+                   int relu, void* stream);
+
+/* ---- GatedConv output (models/networks/GatedUNet.py:303-322): out = feat * sigmoid(gate) and its two gradients ------------------------- */
+int ich_gate_mul_fwd(const void* feat, const void* gate, void* out, int dtype, long long M, void* stream);
+int ich_gate_mul_bwd(const void* feat, const void* gate, const void* dout, void* dfeat, void* dgate, int dtype, long long M, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

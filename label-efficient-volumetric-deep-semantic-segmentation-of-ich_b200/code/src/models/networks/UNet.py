@@ -54,6 +54,11 @@ def _begin_forward():
     _PENDING_NBT.clear()
 
 
+def _was_4d(input):
+    """2-D nets take NCHW (4-D) inputs; an already staged engine tensor [N, 1, H, W, C] carries the flag (ops.staged)."""
+    return input.dim() == 4 or bool(getattr(input, '_ich_was_4d', False))
+
+
 def _not_built(what):
     raise NotImplementedError(f'ich_b200: {what} is not part of the B200 hot path yet (SURVEY section 8f); '
                               f'refusing to fall back silently')
@@ -115,15 +120,15 @@ class ConvBlock(nn.Module):
 
     def forward(self, input):
         _begin_forward()
-        was_4d = input.dim() == 4
+        was_4d = _was_4d(input)
         out = ops.from_channels_last(self.forward_cl(ops.to_channels_last(input)), was_4d)
         _flush_nbt()
         return out
 
 
 class MLPHead(nn.Module):
-    """Linear/ReLU projection head (no ReLU after the last layer). Reference: UNet.py:179-209. B x 256 inputs: plain library
-    GEMMs (cuBLAS via nn.Linear) -- negligible next to the encoder."""
+    """Linear/ReLU projection head (no ReLU after the last layer). Reference: UNet.py:179-209.  The parameters live in nn.Linear
+    sub-modules (state-dict compatible); the arithmetic runs in ich_linear_fwd / ich_linear_bwd (B x 256 matrices: latency-bound)."""
 
     def __init__(self, Neurons_layer=[512, 256, 128]):
         nn.Module.__init__(self)
@@ -132,9 +137,12 @@ class MLPHead(nn.Module):
         self.relu = nn.ReLU()
 
     def forward(self, x):
-        for linear in self.fc_layers[:-1]:
-            x = self.relu(linear(x))
-        return self.fc_layers[-1](x)
+        lead = x.shape[:-1]
+        x = x.reshape(-1, x.shape[-1])
+        n = len(self.fc_layers)
+        for i, linear in enumerate(self.fc_layers):
+            x = ops.Linear.apply(x, linear.weight, linear.bias, i < n - 1)
+        return x.reshape(*lead, x.shape[-1])
 
 
 class ConvHead(nn.Module):
@@ -261,7 +269,7 @@ class UNet(_UNetBase):
 
     def forward(self, input):
         _begin_forward()
-        was_4d = input.dim() == 4
+        was_4d = _was_4d(input)
         x = ops.to_channels_last(input)
         x, res = self._encode(x)
         x_bottleneck = x
@@ -295,7 +303,7 @@ class UNet_Encoder(_UNetBase):
 
     def forward(self, input):
         _begin_forward()
-        was_4d = input.dim() == 4
+        was_4d = _was_4d(input)
         x, _ = self._encode(ops.to_channels_last(input))
         _flush_nbt()
         pooled = ops.GlobalAvgPool.apply(x)                                     # UNet.py:318, fp32 [N, C]
@@ -322,7 +330,7 @@ class Partial_UNet(_UNetBase):
 
     def forward(self, input):
         _begin_forward()
-        was_4d = input.dim() == 4
+        was_4d = _was_4d(input)
         x, res = self._encode(ops.to_channels_last(input))
         x_bottleneck = x
         x = self._decode(x, res[::-1][:self.n_decoder][::-1])                  # UNet.py:425-427

@@ -4,6 +4,7 @@
 // of a wider concat buffer.  Vector path: 16-byte accesses (8 bf16 / 4 fp32) when C, ld and the base are aligned.
 // Replaces ATen batch_norm / relu / max_pool3d / cat behind reference models/networks/UNet.py:82,119,149,154-161.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -1011,17 +1012,20 @@ __global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* _
       float a[V];
       Raw16<T>::unpack(raw[u], a);
       if (gi == 0) gb += dl[u];
+      // The kernel is issue-bound, not HBM-bound (ncu: 2.0 TB/s with 12 instructions per element): the per-channel constants w_head and
+      // invstd are factored out of the sums (applied once after the loop), which leaves 7 instructions per element.
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const float z = fmaf(a[k], sc[k], sf[k]);
-        const bool pos = !relu || z > 0.f;
-        gw[k] = fmaf(dl[u], pos ? z : 0.f, gw[k]);
-        const float g0 = pos ? dl[u] * wk[k] : 0.f;
-        sb[k] += g0;
-        sg[k] = fmaf(g0, (a[k] - mu[k]) * is[k], sg[k]);
+        const float t = (!relu || z > 0.f) ? dl[u] : 0.f;           // d(logit) where the unit is active
+        gw[k] = fmaf(t, z, gw[k]);                                   // head d(w) = sum dl * relu(z)
+        sb[k] += t;                                                  // sum dl * [z > 0]             (x w_head      = d(beta))
+        sg[k] = fmaf(t, a[k] - mu[k], sg[k]);                        // sum dl * [z > 0] * (y - mean) (x w_head*invstd = d(gamma))
       }
     }
   }
+#pragma unroll
+  for (int k = 0; k < V; ++k) { sb[k] *= wk[k]; sg[k] *= wk[k] * is[k]; }
   // lanes that own the same channel group are `groups` apart: butterfly over those, one row of partials per warp, sum over the warps
   extern __shared__ float sh[];  // [8 warps][3][C] + [8]
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -1062,7 +1066,7 @@ __global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* _
 
 // Apply pass: dy = scale * (dz - d(beta)/M - yhat * d(gamma)/M) with dz rebuilt from d(logit); block 0 also publishes d(gamma),
 // d(beta) and the head's d(w), d(b).
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                                      const float* __restrict__ shift, const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, const float* __restrict__ w,
@@ -1072,7 +1076,6 @@ __global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __
                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dw,
                                                                      float* __restrict__ db) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = 4;
   const int groups = C / V, rpb = 256 / groups;
   const int c = (threadIdx.x % groups) * V;
   const float invM = training ? (float)(1.0 / (double)M) : 0.f;
@@ -1094,9 +1097,10 @@ __global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __
   float sc[V], sf[V], k0[V], k1[V], wk[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    sc[k] = scale[c + k]; sf[k] = shift[c + k]; wk[k] = w[c + k];
+    sc[k] = scale[c + k]; sf[k] = shift[c + k];
     k1[k] = sc[k] * invstd[c + k] * tot[C + c + k] * invM;
     k0[k] = sc[k] * tot[c + k] * invM - mean[c + k] * k1[k];
+    wk[k] = sc[k] * w[c + k];                                  // scale * w_head: dy = [z > 0] * dl * (scale * w_head) - (y * k1 + k0)
   }
   const long long step = (long long)gridDim.x * rpb;
   for (long long r0 = (long long)blockIdx.x * rpb + threadIdx.x / groups; r0 < M; r0 += U * step) {
@@ -1121,8 +1125,8 @@ __global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __
       Raw16<T>::unpack(raw[u], a);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const float g0 = (!relu || fmaf(a[k], sc[k], sf[k]) > 0.f) ? dl[u] * wk[k] : 0.f;
-        a[k] = fmaf(sc[k], g0, -fmaf(a[k], k1[k], k0[k]));
+        const float t = (!relu || fmaf(a[k], sc[k], sf[k]) > 0.f) ? dl[u] : 0.f;
+        a[k] = fmaf(t, wk[k], -fmaf(a[k], k1[k], k0[k]));
       }
       if (r < M) Vec<T>::store(dy + r * dy_ld + c, a);
     }
@@ -1503,11 +1507,18 @@ int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, cons
     const int rpb = 256 / (C / Vec<T>::N);
     const size_t sh_reduce = sizeof(float) * (8 * 3 * C + 8), sh_apply = sizeof(float) * 2 * C;
     const int grid_r = one_wave_grid(bn_head_bwd_reduce_rows_kernel<T>, sh_reduce, M, rpb);
-    const int grid_a = one_wave_grid(bn_head_bwd_apply_rows_kernel<T>, sh_apply, M, rpb);
+    static int apply_u = -1;          // rows in flight per thread of the apply pass: 4 (default) or 8 (ICH_HEAD_APPLY_U=8, A/B switch)
+    if (apply_u < 0) { const char* e = getenv("ICH_HEAD_APPLY_U"); apply_u = (e && atoi(e) == 8) ? 8 : 4; }
+    const int grid_a = apply_u == 8 ? one_wave_grid(bn_head_bwd_apply_rows_kernel<T, 8>, sh_apply, M, rpb)
+                                    : one_wave_grid(bn_head_bwd_apply_rows_kernel<T, 4>, sh_apply, M, rpb);
     bn_head_bwd_reduce_rows_kernel<T><<<grid_r, 256, sh_reduce, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C, relu, act, sums,
                                                                      hsums);
-    bn_head_bwd_apply_rows_kernel<T><<<grid_a, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
-                                                                   dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+    if (apply_u == 8)
+      bn_head_bwd_apply_rows_kernel<T, 8><<<grid_a, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
+                                                                        dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+    else
+      bn_head_bwd_apply_rows_kernel<T, 4><<<grid_a, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
+                                                                        dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
   })
   return ich_check_launch("ich_bn_head_bwd");
 }

@@ -14,12 +14,12 @@ REPO_ROOT = os.path.dirname(PKG_ROOT)
 CSRC = os.path.join(PKG_ROOT, 'csrc')
 HEADER = os.path.join(REPO_ROOT, 'include', 'ich_b200.h')
 LIB_PATH = os.path.join(_HERE, 'libich_b200.so')
-SOURCES = ['api.cu', 'gemm_generic.cu', 'elementwise.cu', 'loss.cu', 'conv_tc.cu', 'conv_tc_stream.cu', 'conv_cin1_tc.cu']
+SOURCES = ['api.cu', 'gemm_generic.cu', 'elementwise.cu', 'loss.cu', 'conv_tc.cu', 'conv_tc_stream.cu', 'conv_cin1_tc.cu', 'aux_ops.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 
-_CTYPE = {'int': ctypes.c_int, 'long long': ctypes.c_longlong, 'float': ctypes.c_float, 'double': ctypes.c_double,
+_CTYPE = {'int': ctypes.c_int, 'unsigned char': ctypes.c_ubyte, 'long long': ctypes.c_longlong, 'float': ctypes.c_float, 'double': ctypes.c_double,
           'unsigned int': ctypes.c_uint}
 
 

@@ -24,9 +24,9 @@ _state = {
     # (measured at cfg-3: 15.57 -> 15.19 ms/step, end to end 16.25 -> 15.99; 0 = separate BN-apply / head kernels)
     'fuse_head': os.environ.get('ICH_B200_FUSE_HEAD', '1') == '1',
     # inference (eval mode under torch.no_grad): fold BatchNorm into the conv weights, one conv launch with a bias + ReLU epilogue per
-    # unit instead of conv + bn_finalize + BN-apply (ops.folded_eval_unit).  Host logic over kernels that are already parity-tested;
-    # not yet timed on a GPU -> off by default
-    'fold_eval_bn': os.environ.get('ICH_B200_FOLD_EVAL_BN', '0') == '1',
+    # unit instead of conv + bn_finalize + BN-apply (ops.folded_eval_unit).  Parity at cfg-5's real size with and without folding:
+    # tests/test_parity_r2.py::test_cfg5_full_volume_sliding_window; measured 5.38 -> 4.56 ms per 32x512x512 volume.  0 = unfolded.
+    'fold_eval_bn': os.environ.get('ICH_B200_FOLD_EVAL_BN', '1') == '1',
     # re-derive the kernel-layout weight packs from a global optimizer post-step hook (hidden behind the GPU's backlog) instead of at
     # the start of the next forward pass (0 = only there)
     'refresh_after_step': os.environ.get('ICH_B200_REFRESH_AFTER_STEP', '1') == '1',

@@ -355,7 +355,6 @@ class ToChannelsLast(Function):
     @staticmethod
     def forward(ctx, x):
         _require_cuda(x, 'ToChannelsLast')
-        refresh_packs()                     # start of a forward pass: re-derive the weight packs the optimizer step invalidated
         x = x.contiguous().float()
         ctx.was_4d = x.dim() == 4
         if ctx.was_4d:
@@ -396,6 +395,9 @@ class FromChannelsLast(Function):
 
 
 def to_channels_last(x):
+    refresh_packs()                         # start of a forward pass: re-derive the weight packs the optimizer step invalidated
+    if getattr(x, '_ich_staged', False):    # already [N, D, H, W, C] in the engine dtype (ops.stage_ct / ops.staged)
+        return x
     return ToChannelsLast.apply(x)
 
 
@@ -873,7 +875,7 @@ class Head(Function):
             db = torch.empty(1, dtype=torch.float32, device=x.device)
             call('ich_head1_bwd', xp, xld, _dt(x), wf.data_ptr(), out.data_ptr(), dout.data_ptr(), _p(dx), cin, dw.data_ptr(), db.data_ptr(),
                  n * s, cin, ctx.act, _stream())
-            return dx, dw.view(weight.shape), db, None
+            return dx, (dw.view(weight.shape) if need[1] else None), (db if need[2] else None), None
         dl = torch.empty((n, d, h, w, cout), dtype=x.dtype, device=x.device)
         call('ich_head_dlogit', out.data_ptr(), dout.data_ptr(), dl.data_ptr(), _dt(x), n, s, cout, ctx.act, _stream())
         dx = conv_dgrad(dl, weight) if need[0] else None
@@ -902,6 +904,113 @@ class GlobalAvgPool(Function):
         dx = torch.empty(ctx.shape, dtype=ctx.dt, device=g.device)
         call('ich_avgpool_bwd', g.data_ptr(), dx.data_ptr(), c, config.dtype_code(ctx.dt), n, d * h * w, c, _stream())
         return dx
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MLPHead layers (models/networks/UNet.py:179-209): Linear (+ReLU) on the pooled [B, C] fp32 matrix
+# ---------------------------------------------------------------------------------------------------------------
+class Linear(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        _require_cuda(x, 'Linear')
+        x = x.contiguous().float()
+        w = weight.detach().contiguous().float()
+        b, k = x.shape
+        n = w.shape[0]
+        out = torch.empty((b, n), dtype=torch.float32, device=x.device)
+        call('ich_linear_fwd', x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), b, k, n, int(relu), _stream())
+        ctx.save_for_backward(x, w, out)
+        ctx.relu, ctx.has_bias = bool(relu), bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, out = ctx.saved_tensors
+        b, k = x.shape
+        n = w.shape[0]
+        dout = dout.contiguous().float()
+        need = ctx.needs_input_grad
+        dx = torch.empty_like(x) if need[0] else None
+        want_w = need[1] or (need[2] and ctx.has_bias)
+        dw = torch.empty_like(w) if want_w else None
+        db = torch.empty(n, dtype=torch.float32, device=x.device) if (want_w and ctx.has_bias) else None
+        call('ich_linear_bwd', dout.data_ptr(), out.data_ptr(), x.data_ptr(), w.data_ptr(), _p(dx), _p(dw), _p(db), b, k, n, int(ctx.relu), _stream())
+        return dx, (dw if need[1] else None), (db if need[2] else None), None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GatedConv output (models/networks/GatedUNet.py:303-322): out = feat * sigmoid(gate)
+# ---------------------------------------------------------------------------------------------------------------
+class GateMul(Function):
+    @staticmethod
+    def forward(ctx, feat, gate):
+        feat, gate = feat.contiguous(), gate.contiguous()
+        out = torch.empty_like(feat)
+        call('ich_gate_mul_fwd', feat.data_ptr(), gate.data_ptr(), out.data_ptr(), _dt(feat), feat.numel(), _stream())
+        ctx.save_for_backward(feat, gate)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, gate = ctx.saved_tensors
+        dout = dout.contiguous()
+        dfeat, dgate = torch.empty_like(feat), torch.empty_like(gate)
+        call('ich_gate_mul_bwd', feat.data_ptr(), gate.data_ptr(), dout.data_ptr(), dfeat.data_ptr(), dgate.data_ptr(), _dt(feat), feat.numel(), _stream())
+        return dfeat, dgate
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# input staging + sliding-window plumbing
+# ---------------------------------------------------------------------------------------------------------------
+_SRC_DTYPE = {torch.float32: 0, torch.int16: 1, torch.uint16: 2, torch.uint8: 3}
+
+
+def stage_ct(raw, win_center=40, win_width=120, out_range=(0, 1), dtype=None):
+    """utils/ct_utils.py:13-36 (window / rescale / clip) + `.float()` + the cast to the engine dtype in one pass over a raw CT tensor on
+    the device (int16 / uint16 / uint8 / fp32, any shape).  Returns a tensor of the same shape in `dtype` (default: the engine dtype).
+    For a one-channel input [N, 1, D, H, W] the result viewed as [N, D, H, W, 1] IS the engine's channel-last layout (see `staged`)."""
+    _require_cuda(raw, 'stage_ct')
+    if raw.dtype not in _SRC_DTYPE:
+        raw = raw.float()
+    raw = raw.contiguous()
+    dtype = dtype or config.act_dtype()
+    out = torch.empty(raw.shape, dtype=dtype, device=raw.device)
+    lo, hi = win_center - win_width / 2, win_center + win_width / 2
+    call('ich_stage_ct', raw.data_ptr(), _SRC_DTYPE[raw.dtype], out.data_ptr(), config.dtype_code(dtype), raw.numel(), float(lo), float(hi),
+         float(out_range[0]), float(out_range[1]), _stream())
+    return out
+
+
+def staged(x_cl, was_4d=False):
+    """Mark an engine-layout tensor [N, D, H, W, C] (engine dtype) so that the drop-in networks take it as is instead of converting from
+    NC(D)HW fp32 (ops.to_channels_last passes it through).  was_4d: the logical input is NCHW (2-D nets, D = 1), so the network
+    output is squeezed back to 4-D."""
+    if x_cl.dim() != 5 or x_cl.dtype != config.act_dtype():
+        raise RuntimeError(f'ich_b200.staged: expected [N, D, H, W, C] in {config.act_dtype()}, got {tuple(x_cl.shape)} {x_cl.dtype}')
+    x_cl._ich_staged = True
+    x_cl._ich_was_4d = bool(was_4d)
+    return x_cl
+
+
+def window_gather(vol, starts, window):
+    """vol [D, H, W] (one channel, any engine dtype) + starts int32 [n, 3] on the device -> windows [n, wd, wh, ww, 1]."""
+    d, h, w = vol.shape
+    n = starts.shape[0]
+    out = torch.empty((n,) + tuple(window) + (1,), dtype=vol.dtype, device=vol.device)
+    call('ich_window_gather', vol.data_ptr(), _dt(vol), d, h, w, starts.data_ptr(), n, *window, out.data_ptr(), _stream())
+    return out
+
+
+def window_scatter(pred, starts, window, shape, overlap, threshold, acc, cnt, mask):
+    """Stitch window predictions fp32 [n, 1, wd, wh, ww] into the volume buffers (see ich_window_scatter)."""
+    d, h, w = shape
+    pred = pred.contiguous().float()
+    call('ich_window_scatter', pred.data_ptr(), d, h, w, starts.data_ptr(), starts.shape[0], *window, int(overlap), float(threshold),
+         _p(acc), _p(cnt), _p(mask), _stream())
+
+
+def blend_threshold(acc, cnt, threshold, mask):
+    call('ich_blend_threshold', acc.data_ptr(), cnt.data_ptr(), acc.numel(), float(threshold), _p(mask), _stream())
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -50,7 +50,7 @@ TABLE = {
     'ich_space_to_depth2_sum': _bw('space_to_depth', lambda a: 2 * _vox(a) * 4 * a['FD'] * a['C'] * _es(a)),
     'ich_layout_nc_to_nl': _bw('layout', lambda a: a['N'] * a['C'] * a['S'] * (4 + _es(a))),
     'ich_layout_nl_to_nc': _bw('layout', lambda a: a['N'] * a['C'] * a['S'] * (4 + _es(a))),
-    'ich_stage_ct': _bw('layout', lambda a: a['M'] * (a['src_bytes'] + _es(a))),
+    'ich_stage_ct': _bw('layout', lambda a: a['M'] * ((4, 2, 2, 1)[a['src_dtype']] + _es(a))),
     'ich_head_fwd': _bw('head', lambda a: a['N'] * a['S'] * (a['Cin'] * _es(a) + 4 * a['Cout'])),
     'ich_head1_bwd': _bw('head', lambda a: a['M'] * (a['Cin'] * _es(a) * (2 if a.get('dx') else 1) + 8)),
     'ich_bn_head_fwd': _bw('head', lambda a: a['M'] * (a['C'] * _es(a) + 4)),

@@ -94,7 +94,12 @@ class DevicePrefetcher:
 
 
 def window_ct(ct_scan, win_center=40, win_width=120, out_range=(0, 1)):
-    """utils/ct_utils.py:13-36 on a torch tensor (any device): rescale [center - width/2, center + width/2] to out_range, clip."""
+    """utils/ct_utils.py:13-36 on a torch tensor: rescale [center - width/2, center + width/2] to out_range, clip.  CUDA tensors
+    (int16 / uint16 / uint8 / fp32 Hounsfield units) go through the staging kernel (`ops.stage_ct`, one pass, fp32 result; pass
+    dtype there to get the engine dtype directly); CPU tensors take the torch expression below (host-side pipelines)."""
+    if ct_scan.is_cuda:
+        from . import ops
+        return ops.stage_ct(ct_scan, win_center, win_width, out_range, dtype=torch.float32)
     win_min = win_center - win_width / 2
     win_max = win_center + win_width / 2
     out = (out_range[1] - out_range[0]) * (ct_scan.float() - win_min) / (win_max - win_min) + out_range[0]

@@ -74,6 +74,65 @@ def tversky_fixtures(ref_loss, LO, report):
     torch.save(dict(pred=pred, mask=mask, cases=cases), os.path.join(OUT, 'tversky.pt'))
 
 
+def window_ct_fixture(report):
+    """utils/ct_utils.py:13-36 run on Hounsfield-unit arrays of the dtypes a CT pipeline holds (int16 / uint16 / uint8 / fp32)."""
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == 'src' or k.startswith('src.')]:
+        del sys.modules[k]
+    ct_utils = importlib.import_module('src.utils.ct_utils')
+    sys.path.remove(REF)
+    sys.path.insert(0, ROOT)
+    from oracle import ct_oracle as CO
+    rng = np.random.RandomState(0)
+    cases = []
+    for dtype, lo, hi in ((np.int16, -1200, 3000), (np.uint16, 0, 4095), (np.uint8, 0, 255), (np.float32, -1200, 3000)):
+        hu = rng.uniform(lo, hi, size=(3, 17, 19)).astype(dtype)
+        for center, width, rng_out in ((40, 120, (0, 1)), (50, 100, (0, 255)), (600, 2800, (0, 1))):
+            want = ct_utils.window_ct(hu.astype(np.float64), win_center=center, win_width=width, out_range=rng_out)
+            got = CO.window_ct(hu, center, width, rng_out)
+            report[f'window_ct/{np.dtype(dtype).name}/{center}-{width}'] = float(np.abs(got - want).max())
+            cases.append(dict(hu=torch.from_numpy(hu.astype(np.int32 if dtype == np.uint16 else dtype)), dtype=np.dtype(dtype).name, center=center, width=width,
+                              out_range=rng_out, out=torch.from_numpy(want)))
+    torch.save(cases, os.path.join(OUT, 'window_ct.pt'))
+
+
+def gated_unet_fixtures(report):
+    """models/networks/GatedUNet.py: UNet(use_gatedConv=True / False) -- the ad-attention side-track's U-Net (ConvLayer / GatedConv
+    blocks, bilinear decoder when gated).  Golden forward / loss / gradients for the drop-in's GatedUNet."""
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == 'src' or k.startswith('src.')]:
+        del sys.modules[k]
+    gated = importlib.import_module('src.models.networks.GatedUNet')
+    losses = importlib.import_module('src.models.optim.LossFunctions')
+    sys.path.remove(REF)
+    out = {}
+    for name, kw, shape in (('gated2d', dict(depth=3, use_3D=False, in_channels=2, out_channels=1, top_filter=8, midchannels_factor=2, p_dropout=0.0,
+                                              use_gatedConv=True), (2, 2, 16, 16)),
+                            ('plain3d', dict(depth=3, use_3D=True, in_channels=1, out_channels=1, top_filter=8, midchannels_factor=2, p_dropout=0.0,
+                                             use_gatedConv=False), (2, 1, 8, 16, 16)),
+                            ('gated3d', dict(depth=3, use_3D=True, in_channels=1, out_channels=2, top_filter=8, midchannels_factor=1, p_dropout=0.0,
+                                             use_gatedConv=True), (1, 1, 8, 16, 16))):
+        torch.manual_seed(5)
+        net = gated.UNet(**kw).train()
+        g = torch.Generator().manual_seed(5)
+        x = torch.rand(*shape, generator=g)
+        oshape = (shape[0], kw['out_channels']) + tuple(shape[2:])
+        mask = (torch.rand(*oshape, generator=g) > 0.8).float()
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        lossf = losses.BinaryDiceLoss(reduction='mean', p=2, alpha=1.0)
+        o = net(x)
+        loss = lossf(o, mask)
+        loss.backward()
+        sd1 = {k: v.clone() for k, v in net.state_dict().items()}
+        net.eval()
+        with torch.no_grad():
+            oe = net(x)
+        out[name] = dict(kwargs=kw, x=x, mask=mask, state_dict=sd0, out_train=o.detach(), loss=loss.detach(), grads=grads_of(net),
+                         state_dict_after=sd1, out_eval=oe, loss_kwargs=dict(reduction='mean', p=2, alpha=1.0))
+        report[f'gated_unet/{name}/n_keys'] = 0.0
+    torch.save(out, os.path.join(OUT, 'gated_unet.pt'))
+
+
 def main():
     sys.path.insert(0, ROOT)
     from oracle import unet_oracle as UO, losses_oracle as LO
@@ -81,11 +140,16 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
     report = {}
-    if '--bilinear-only' in sys.argv or '--tversky-only' in sys.argv:      # add fixtures without rewriting the others
-        if '--bilinear-only' in sys.argv:
+    only = [a for a in sys.argv if a in ('--bilinear-only', '--tversky-only', '--window-ct-only', '--gated-only')]
+    if only:      # add fixtures without rewriting the others
+        if '--bilinear-only' in only:
             bilinear_fixtures(ref_unet, ref_loss, UO, LO, report)
-        else:
+        if '--tversky-only' in only:
             tversky_fixtures(ref_loss, LO, report)
+        if '--window-ct-only' in only:
+            window_ct_fixture(report)
+        if '--gated-only' in only:
+            gated_unet_fixtures(report)
         for k, v in report.items():
             print(f'{k:60s} oracle-vs-reference {v:.3e}')
         assert max(report.values()) < 5e-5

@@ -80,9 +80,19 @@ def _worker(rank, world, port, out):
         vol = torch.rand(1, 1, 8, 16, 16)
         net.eval()
         dp.broadcast_state(net)                              # per-rank BatchNorm buffers diverged during training (DDP semantics)
-        pred_d, mask_d = infer.sliding_window_predict(net, vol, (4, 8, 8), (4, 4, 8), batch=2, distributed=True)
-        pred_s, mask_s = infer.sliding_window_predict(net, vol, (4, 8, 8), (4, 4, 8), batch=3, distributed=False)
-        assert torch.allclose(pred_d, pred_s, atol=1e-6) and torch.equal(mask_d, mask_s)
+        from ich_b200 import config as _config, ops as _ops
+        import host_mocks
+        host_mocks.install_window_mocks(_ops, infer)         # the window kernels replaced by CPU stand-ins: host logic only
+        wnet = host_mocks.ChannelLastAdapter(net)
+        with _config.override(precision='fp32'):
+            pred_d, mask_d = infer.sliding_window_predict(wnet, vol, (4, 8, 8), (4, 4, 8), batch=2, distributed=True)
+            pred_s, mask_s = infer.sliding_window_predict(wnet, vol, (4, 8, 8), (4, 4, 8), batch=3, distributed=False)
+            assert torch.allclose(pred_d, pred_s, atol=1e-6) and torch.equal(mask_d, mask_s)
+            # disjoint windows: only the uint8 mask is exchanged (and the prediction when asked for)
+            pred_d, mask_d = infer.sliding_window_predict(wnet, vol, (4, 8, 8), batch=2, distributed=True)
+            none_d, mask_m = infer.sliding_window_predict(wnet, vol, (4, 8, 8), batch=2, distributed=True, return_pred=False)
+            pred_s, mask_s = infer.sliding_window_predict(wnet, vol, (4, 8, 8), batch=3, distributed=False)
+            assert none_d is None and torch.equal(mask_m, mask_s) and torch.equal(mask_d, mask_s) and torch.allclose(pred_d, pred_s, atol=1e-6)
         assert sorted(sum((dp.shard_indices(7, r, world) for r in range(world)), [])) == list(range(7))
 
         # cross-rank contrastive set (ICH_B200_GLOBAL_NCE): gather_rows over gloo; the loss is evaluated identically on every rank,
@@ -167,11 +177,19 @@ def test_sliding_window_matches_oracle_rule_single_process():
         def forward(self, x):
             return UO.unet_forward(x, sd, use_3D=True, training=False)
 
-    vol = torch.rand(1, 1, 8, 32, 16, generator=torch.Generator().manual_seed(3))
-    for window, stride in (((8, 16, 16), (8, 16, 16)), ((8, 16, 16), (8, 8, 8)), ((4, 16, 8), (4, 12, 8))):
-        got, gm = infer.sliding_window_predict(OracleNet(), vol, window, stride, batch=3, distributed=False)
-        want, wm = UO.sliding_window_predict(vol, sd, window, stride)
-        assert torch.allclose(got, want, atol=1e-6) and torch.equal(gm, wm)
+    from ich_b200 import config as _config, ops as _ops
+    import host_mocks
+    saved = (_ops.window_gather, _ops.window_scatter, _ops.blend_threshold, infer._cast)
+    host_mocks.install_window_mocks(_ops, infer)             # the window kernels replaced by CPU stand-ins: host logic only
+    try:
+        vol = torch.rand(1, 1, 8, 32, 16, generator=torch.Generator().manual_seed(3))
+        with _config.override(precision='fp32'):
+            for window, stride in (((8, 16, 16), (8, 16, 16)), ((8, 16, 16), (8, 8, 8)), ((4, 16, 8), (4, 12, 8))):
+                got, gm = infer.sliding_window_predict(host_mocks.ChannelLastAdapter(OracleNet()), vol, window, stride, batch=3, distributed=False)
+                want, wm = UO.sliding_window_predict(vol, sd, window, stride)
+                assert torch.allclose(got, want, atol=1e-6) and torch.equal(gm, wm)
+    finally:
+        _ops.window_gather, _ops.window_scatter, _ops.blend_threshold, infer._cast = saved
 
 
 def test_prefetcher_and_window_ct_host_logic():

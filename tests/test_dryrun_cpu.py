@@ -239,3 +239,90 @@ def test_frozen_parameters_skip_their_weight_gradients(dry):
     assert len([n for n in dry.trace if 'wgrad' in n]) < len(wgrads)
     assert all(p.grad is None for p in net.down_block.parameters())
     assert all(p.grad is not None for p in net.up_block.parameters())
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+def test_gated_unet_plumbing(dry, prec, golden):
+    """Drop-in GatedUNet (reference models/networks/GatedUNet.py): state-dict keys of the golden runs load, and forward + backward flow
+    through ConvBnRelu / ConvBias / GateMul / UpsampleCat / Head for the gated and the plain variant."""
+    from src.models.networks.GatedUNet import UNet, GatedConv, ConvLayer
+    from src.models.optim.LossFunctions import BinaryDiceLoss
+    fxs = golden('gated_unet.pt')
+    with config.override(precision=prec):
+        for name, fx in fxs.items():
+            net = UNet(**fx['kwargs'])
+            assert list(net.state_dict().keys()) == list(fx['state_dict'].keys()), name
+            net.load_state_dict(fx['state_dict'])
+            net.train()
+            dry.trace.clear()
+            out = net(fx['x'])
+            assert out.shape == fx['out_train'].shape and out.dtype == torch.float32
+            BinaryDiceLoss(**fx['loss_kwargs'])(out, fx['mask']).backward()
+            _grads_ok(net)
+            gated = fx['kwargs']['use_gatedConv']
+            assert ('ich_gate_mul_fwd' in dry.trace) == gated and ('ich_gate_mul_bwd' in dry.trace) == gated
+            assert ('ich_upsample2_fwd' in dry.trace) == gated
+            assert isinstance(net.down_block[0].conv1, GatedConv if gated else ConvLayer)
+    with pytest.raises(NotImplementedError):
+        UNet(depth=3, top_filter=8, p_dropout=0.5, use_gatedConv=True).train()(torch.rand(1, 1, 16, 16))
+    with pytest.raises(NotImplementedError):
+        ConvLayer(4, 4, 3, padding=1, activation='lrelu')(torch.rand(1, 4, 8, 8))
+
+
+def test_mlp_head_runs_on_the_engine(dry):
+    from src.models.networks.UNet import MLPHead, UNet_Encoder
+    head = MLPHead([32, 16, 8])
+    out = head(torch.rand(4, 32))
+    assert out.shape == (4, 8)
+    out.sum().backward()
+    _grads_ok(head)
+    assert dry.trace.count('ich_linear_fwd') == 2 and dry.trace.count('ich_linear_bwd') == 2
+    dry.trace.clear()
+    enc = UNet_Encoder(depth=3, use_3D=True, top_filter=16, MLP_head=[32, 8], p_dropout=0.0).train()
+    enc(torch.rand(2, 1, 8, 16, 16)).sum().backward()
+    _grads_ok(enc)
+    assert 'ich_linear_fwd' in dry.trace and 'ich_avgpool_fwd' in dry.trace
+
+
+def test_staging_and_volume_inference_plumbing(dry):
+    """ops.stage_ct / staged inputs / window gather-scatter / segement_volume: argument plumbing against the header prototypes."""
+    from ich_b200 import infer
+    from src.models.networks.UNet import UNet
+    with config.override(precision='bf16'):
+        raw = torch.randint(-1000, 2000, (6, 16, 16), dtype=torch.int16)
+        x = ops.stage_ct(raw, 40, 120, (0, 1))
+        assert x.dtype == torch.bfloat16 and x.shape == raw.shape and dry.trace[-1] == 'ich_stage_ct'
+        with pytest.raises(RuntimeError):
+            ops.staged(torch.zeros(1, 1, 4, 4))                      # not an engine-layout tensor
+        net3 = UNet(depth=3, use_3D=True, top_filter=16, midchannels_factor=2, p_dropout=0.0).eval()
+        vol = torch.rand(1, 1, 8, 32, 16)
+        for stride, ret in (((8, 16, 16), True), ((8, 16, 16), False), ((4, 8, 8), True)):
+            dry.trace.clear()
+            pred, mask = infer.sliding_window_predict(net3, vol, (8, 16, 16), stride, batch=3, distributed=False, return_pred=ret)
+            assert mask.shape == vol.shape and mask.dtype == torch.bool and (pred is None) == (not ret)
+            assert 'ich_window_gather' in dry.trace and 'ich_window_scatter' in dry.trace
+            assert ('ich_blend_threshold' in dry.trace) == (stride != (8, 16, 16))
+            assert 'ich_layout_nc_to_nl' not in dry.trace          # windows enter the network already in the engine layout
+        # segement_volume: 2-D net on every slice, 3-D net on windows; [H, W, S] int16 Hounsfield units in, uint8 0 / 255 out
+        hu = np.random.RandomState(0).randint(-1000, 2000, size=(16, 32, 5)).astype(np.int16)
+        net2 = UNet(depth=3, use_3D=False, top_filter=16, midchannels_factor=1, p_dropout=0.0).eval()
+        dry.trace.clear()
+        seg = infer.segement_volume(net2, hu, window=(40, 120), input_size=(32, 16), return_pred=True, batch_size=2, device='cpu')
+        assert seg.shape == hu.shape and seg.dtype == np.uint8 and dry.trace.count('ich_stage_ct') == 1
+        assert dry.trace.count('ich_bn_head_fwd') == 3              # 5 slices in batches of 2
+        seg3 = infer.segement_volume(net3, np.zeros((16, 32, 8), np.int16), window=(40, 120), return_pred=True, device='cpu', window_3d=(8, 16, 16))
+        assert seg3.shape == (16, 32, 8)
+        assert infer.segement_volume(net2, hu, window=None, input_size=None, device='cpu') is None
+
+
+def test_graphed_step_needs_fresh_optimizer():
+    from ich_b200.graph import GraphedStep
+    lin = torch.nn.Linear(4, 4)
+    opt = torch.optim.Adam(lin.parameters())
+    step = GraphedStep(lambda x: x, opt)
+    assert all(g['capturable'] for g in opt.param_groups) and step.graph is None
+    lin(torch.rand(2, 4)).sum().backward()
+    opt2 = torch.optim.Adam(lin.parameters())
+    opt2.step()
+    with pytest.raises(RuntimeError):
+        GraphedStep(lambda x: x, opt2)

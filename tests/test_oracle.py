@@ -117,3 +117,25 @@ def test_bilinear_decoders(golden):
                 continue
             assert (sd[k].grad - g).norm() / (g.norm() + 1e-12) < 1e-3, (name, k)
 
+
+
+def test_window_ct_vectors(golden):
+    """oracle/ct_oracle.window_ct against utils/ct_utils.py:13-36 run on int16 / uint16 / uint8 / fp32 Hounsfield-unit arrays."""
+    import numpy as np
+    from oracle import ct_oracle as CO
+    cases = golden('window_ct.pt')
+    assert len(cases) == 12
+    for c in cases:
+        got = CO.window_ct(c['hu'].numpy(), c['center'], c['width'], c['out_range'])
+        assert np.array_equal(got, c['out'].numpy()), (c['dtype'], c['center'])
+
+
+def test_segment_volume_slices_rule():
+    """Slice-wise volume segmentation rule (UNet2D.py:272-314 without resize / NIfTI): rotation there and back, batching, 0 / 255."""
+    import numpy as np
+    from oracle import ct_oracle as CO
+    hu = np.random.RandomState(1).randint(-100, 200, size=(6, 4, 5)).astype(np.int16)
+    fwd = lambda x: (x > 0.5).float()                                  # a "network" that thresholds the windowed input
+    seg = CO.segment_volume_slices(hu, fwd, window=(40, 120), batch_size=2)
+    want = ((CO.window_ct(hu, 40, 120) > 0.5) * 255).astype(np.uint8)  # rot90 there and back is the identity on a pointwise rule
+    assert seg.shape == hu.shape and np.array_equal(seg, want)
