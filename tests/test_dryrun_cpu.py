@@ -131,7 +131,7 @@ def test_unet2d_variants_plumbing(dry, kw):
 
 def test_folded_eval_bn_plumbing(dry):
     """ICH_B200_FOLD_EVAL_BN: under eval + no_grad every unit but the fused last one is ONE conv launch (BatchNorm folded into the
-    weights, bias + ReLU epilogue); training mode, eval with autograd and the default configuration keep the BatchNorm kernels.
+    weights, bias + ReLU epilogue; the default since round 2); training mode, eval with autograd and ICH_B200_FOLD_EVAL_BN=0 keep the BatchNorm kernels.
     The folded weights are a cache keyed on the versions of the tensors they derive from."""
     from src.models.networks.UNet import UNet
     x = torch.rand(1, 1, 8, 16, 16)
@@ -166,7 +166,12 @@ def test_folded_eval_bn_plumbing(dry):
     dry.trace.clear()
     with torch.no_grad():
         net(x)
-    assert dry.trace.count('ich_bn_finalize') == 10                 # default: off
+    assert dry.trace.count('ich_bn_finalize') == 1                  # default: on (round 2, after the full-size cfg-5 parity run)
+    with config.override(fold_eval_bn=False):
+        dry.trace.clear()
+        with torch.no_grad():
+            net(x)
+        assert dry.trace.count('ich_bn_finalize') == 10             # ICH_B200_FOLD_EVAL_BN=0: the BatchNorm kernels
 
 
 def test_weight_packs_refreshed_from_the_optimizer_hook(dry, monkeypatch):
