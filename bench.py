@@ -153,9 +153,10 @@ class Job:
     """One workload on one device for one arm.  `host` = this rank's step inputs in (pinned) host memory; `step(*device_inputs)` runs one
     step and returns a tensor whose value the end-to-end pass reads back (the loss, or the predicted mask)."""
 
-    def __init__(self, wl, nets, losses, dev, rank, batch, spatial, arm, cudnn_mode='bf16', world=1):
+    def __init__(self, wl, nets, losses, dev, rank, batch, spatial, arm, cudnn_mode='bf16', world=1, shard='volume'):
         import numpy as np
         self.wl, self.arm, self.dev, self.kind = wl, arm, dev, wl['kind']
+        self.shard_windows = shard == 'window' and world > 1 and wl['kind'] == 'infer' and arm == 'b200' 
         self.rank, self.np = rank, np
         torch.manual_seed(0)
         net = getattr(nets, wl['net'])(**wl['net_kw']).to(dev)
@@ -170,7 +171,7 @@ class Job:
                 net = net.to(memory_format=self.fmt)
         self.net = net.eval() if self.kind == 'infer' else net.train()
         self.opt = None if self.kind == 'infer' else torch.optim.Adam(net.parameters(), lr=1e-3)
-        g = torch.Generator().manual_seed(rank)
+        g = torch.Generator().manual_seed(0 if self.shard_windows else rank)      # window sharding: every rank holds the SAME volume
         shape = (batch, 1) + tuple(spatial)
         pin = (lambda t: t.pin_memory()) if dev.type == 'cuda' else (lambda t: t)
         self.units = batch
@@ -211,7 +212,7 @@ class Job:
         if self.kind == 'infer':
             if self.arm == 'b200':
                 from ich_b200 import infer
-                return infer.sliding_window_predict(self.net, inp[0], self.wl['window'], batch=8, distributed=False)[1]
+                return infer.sliding_window_predict(self.net, inp[0], self.wl['window'], batch=8, distributed=self.shard_windows, return_pred=False)[1]
             return plain_sliding_window(self._fwd, inp[0], self.wl['window'], 8)
         self.opt.zero_grad()
         if self.kind == 'seg':
@@ -336,6 +337,9 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
     ap.add_argument('--graph', type=int, default=int(os.environ.get('ICH_B200_CUDA_GRAPH', '0')),
                     help='1 = run the training step through ich_b200.graph.GraphedStep (CUDA-graph replay)')
+    ap.add_argument('--shard', default='volume', choices=['volume', 'window'],
+                    help='cfg5 at N > 1: one volume per GPU-step (weak scaling, no data-path collective) or the windows of ONE volume sharded '
+                         'over the ranks with a uint8 mask exchange (strong scaling)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
@@ -366,11 +370,12 @@ def main():
         from ich_b200 import config, dp, _lib, profile
         config.set(precision=args.precision)
         nets, losses = import_modules(os.path.join(PKG, 'code'))
-        job = Job(wl, nets, losses, dev, rank, batch, wl['shape'], 'b200', world=world)
+        job = Job(wl, nets, losses, dev, rank, batch, wl['shape'], 'b200', world=world, shard=args.shard)
         if job.opt is not None:
             dp.install(job.net)
     dev_in = [t.to(dev) for t in job.host]
-    units_step = world * job.units
+    strong = bool(getattr(job, 'shard_windows', False))
+    units_step = job.units if strong else world * job.units
 
     step_fn = job.step
     if args.graph and args.impl == 'b200' and job.opt is not None:
@@ -460,10 +465,11 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in job.host)
         line = {
             'metric': METRIC, 'value': units_step * args.steps / t_dev, 'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': ('bf16' if args.precision == 'bf16' else 'f32') if args.impl == 'b200' else ('bf16' if args.cudnn_mode == 'bf16' else 'tf32'),
+            'warmup': args.warmup, 'ms_per_step': 1e3 * t_dev / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak',
+            'vs_baseline': None, 'dtype': ('bf16' if args.precision == 'bf16' else 'f32') if args.impl == 'b200' else ('bf16' if args.cudnn_mode == 'bf16' else 'tf32'),
             'data': 'synthetic', 'config': {'workload': wl['desc']},
-            'run': {'global_batch': world * batch, 'parallelism': f'dp{world}', 'cuda_graph': bool(args.graph),
+            'run': {'global_batch': world * batch, 'parallelism': f'dp{world}' + (' (windows of one volume sharded, uint8 mask all-reduce)' if strong else ''),
+                    'cuda_graph': bool(args.graph),
                     'l2': 'working set per step (GBs of activations) >> 126 MB L2, no flush needed'},
             'e2e': {'value': units_step * args.steps / t_e2e, 'unit': 'voxels/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h[0], 'ms_per_step': 1e3 * t_e2e / args.steps},

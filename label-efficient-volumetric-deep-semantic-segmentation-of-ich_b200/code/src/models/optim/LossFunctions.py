@@ -126,9 +126,30 @@ class LocalInfoNCELoss(nn.Module):
                 out[b, h0:h0 + self.K, w0:w0 + self.K] = a + 1
         return out
 
+    def _corners_to_device(self, corners, device):
+        """Region corners (drawn on the host from numpy's global RNG, as the reference does) -> device WITHOUT a host synchronisation:
+        a copy from pageable memory blocks the host until the stream reaches it (i.e. until both forward passes have finished), after
+        which the whole backward pass is launched into an idle GPU.  Ring of pinned staging buffers, each guarded by an event."""
+        t = torch.from_numpy(corners)
+        if torch.device(device).type != 'cuda':
+            return t.to(device)
+        ring = getattr(self, '_corner_ring', None)
+        if ring is None or ring[0][0].shape != t.shape:
+            ring = [[torch.empty(t.shape, dtype=t.dtype).pin_memory(), None] for _ in range(4)]
+            self._corner_ring, self._corner_turn = ring, 0
+        slot = ring[self._corner_turn % len(ring)]
+        self._corner_turn += 1
+        if slot[1] is not None:
+            slot[1].synchronize()          # the copy that last used this pinned buffer (4 calls ago) has completed
+        slot[0].copy_(t)
+        out = slot[0].to(device, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return out
+
     def forward(self, f1, f2):
         bs, H, W, C = f1.shape       # dims are read as (bs, H, W, C) whatever the caller meant (SURVEY a14)
-        corners = torch.from_numpy(self.sample_region_corners(tuple(f1.shape))).to(f1.device)
+        corners = self._corners_to_device(self.sample_region_corners(tuple(f1.shape)), f1.device)
         p = ops.RegionGather.apply(f1, f2, corners, self.K)   # [bs, 2A, K*K*C]
         return ops.InfoNCE.apply(p, self.tau)
 

@@ -973,21 +973,20 @@ __global__ void __launch_bounds__(256, 3) bn_head_fwd_rows_kernel(const T* __res
 
 // Reduction pass: d(beta) = sum dz, d(gamma) = sum dz * yhat (into the replicated fp64 `sums` of the BN-backward kernels) and the head's
 // d(w) = sum z * dl, d(b) = sum dl (into `hsums`, [BN_COPIES][C + 1] fp64), with dl = d(logit) and dz = dl * w_head * [z > 0].
-template <typename T>
-__global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+template <typename T, int U>
+__global__ void __launch_bounds__(256, U == 8 ? 2 : 3) bn_head_bwd_reduce_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                                       const float* __restrict__ shift, const float* __restrict__ mean,
                                                                       const float* __restrict__ invstd, const float* __restrict__ w,
                                                                       const float* __restrict__ out, const float* __restrict__ dout, long long M,
                                                                       int C, int relu, int act, double* __restrict__ sums,
                                                                       double* __restrict__ hsums) {
   constexpr int V = Vec<T>::N;
-  constexpr int U = 8;
   const int groups = C / V, rpb = 256 / groups;
   const int gi = threadIdx.x % groups, c = gi * V;
-  float sc[V], sf[V], mu[V], is[V], wk[V], sb[V], sg[V], gw[V];
+  float sc[V], sf[V], mu[V], sb[V], sg[V], gw[V];      // w_head and invstd are applied after the loop: not live across it
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    sc[k] = scale[c + k]; sf[k] = shift[c + k]; mu[k] = mean[c + k]; is[k] = invstd[c + k]; wk[k] = w[c + k];
+    sc[k] = scale[c + k]; sf[k] = shift[c + k]; mu[k] = mean[c + k];
     sb[k] = sg[k] = gw[k] = 0.f;
   }
   float gb = 0.f;
@@ -1025,7 +1024,7 @@ __global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* _
     }
   }
 #pragma unroll
-  for (int k = 0; k < V; ++k) { sb[k] *= wk[k]; sg[k] *= wk[k] * is[k]; }
+  for (int k = 0; k < V; ++k) { const float wk = w[c + k]; sb[k] *= wk; sg[k] *= wk * invstd[c + k]; }
   // lanes that own the same channel group are `groups` apart: butterfly over those, one row of partials per warp, sum over the warps
   extern __shared__ float sh[];  // [8 warps][3][C] + [8]
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -1067,7 +1066,7 @@ __global__ void __launch_bounds__(256) bn_head_bwd_reduce_rows_kernel(const T* _
 // Apply pass: dy = scale * (dz - d(beta)/M - yhat * d(gamma)/M) with dz rebuilt from d(logit); block 0 also publishes d(gamma),
 // d(beta) and the head's d(w), d(b).
 template <typename T, int U>
-__global__ void __launch_bounds__(256) bn_head_bwd_apply_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, U == 8 ? 2 : 3) bn_head_bwd_apply_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                                      const float* __restrict__ shift, const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, const float* __restrict__ w,
                                                                      const float* __restrict__ out, const float* __restrict__ dout,
@@ -1506,19 +1505,22 @@ int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, cons
     ICH_REQUIRE(vec_ok<T>(y, y_ld, C) && vec_ok<T>(dy, dy_ld, C), "ich_bn_head_bwd: rows must be 16-byte aligned (ld %d / %d)", y_ld, dy_ld);
     const int rpb = 256 / (C / Vec<T>::N);
     const size_t sh_reduce = sizeof(float) * (8 * 3 * C + 8), sh_apply = sizeof(float) * 2 * C;
-    const int grid_r = one_wave_grid(bn_head_bwd_reduce_rows_kernel<T>, sh_reduce, M, rpb);
-    static int apply_u = -1;          // rows in flight per thread of the apply pass: 4 (default) or 8 (ICH_HEAD_APPLY_U=8, A/B switch)
-    if (apply_u < 0) { const char* e = getenv("ICH_HEAD_APPLY_U"); apply_u = (e && atoi(e) == 8) ? 8 : 4; }
-    const int grid_a = apply_u == 8 ? one_wave_grid(bn_head_bwd_apply_rows_kernel<T, 8>, sh_apply, M, rpb)
-                                    : one_wave_grid(bn_head_bwd_apply_rows_kernel<T, 4>, sh_apply, M, rpb);
-    bn_head_bwd_reduce_rows_kernel<T><<<grid_r, 256, sh_reduce, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C, relu, act, sums,
-                                                                     hsums);
-    if (apply_u == 8)
+    // rows in flight per thread (A/B switch ICH_HEAD_BWD_U): 8 = one wave of 2 resident blocks per SM with 8 chunks in flight per thread,
+    // 4 = up to 8 blocks per SM queued, 4 resident (more warps, fewer bytes in flight per warp -- the shape of the generic BatchNorm kernels)
+    static int bwd_u = -1;
+    if (bwd_u < 0) { const char* e = getenv("ICH_HEAD_BWD_U"); bwd_u = (e && atoi(e) == 8) ? 8 : 4; }
+    if (bwd_u == 8) {
+      const int grid_r = one_wave_grid(bn_head_bwd_reduce_rows_kernel<T, 8>, sh_reduce, M, rpb);
+      const int grid_a = one_wave_grid(bn_head_bwd_apply_rows_kernel<T, 8>, sh_apply, M, rpb);
+      bn_head_bwd_reduce_rows_kernel<T, 8><<<grid_r, 256, sh_reduce, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C, relu, act, sums, hsums);
       bn_head_bwd_apply_rows_kernel<T, 8><<<grid_a, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
                                                                         dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
-    else
-      bn_head_bwd_apply_rows_kernel<T, 4><<<grid_a, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
-                                                                        dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+    } else {
+      const int grid = rows_grid(M, C, Vec<T>::N);
+      bn_head_bwd_reduce_rows_kernel<T, 4><<<grid, 256, sh_reduce, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C, relu, act, sums, hsums);
+      bn_head_bwd_apply_rows_kernel<T, 4><<<grid, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
+                                                                      dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+    }
   })
   return ich_check_launch("ich_bn_head_bwd");
 }

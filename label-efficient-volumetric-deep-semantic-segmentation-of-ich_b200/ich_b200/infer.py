@@ -61,7 +61,9 @@ def sliding_window_predict(net, vol, window, stride=None, batch=4, threshold=0.5
         raise RuntimeError('ich_b200.infer: the window driver takes one-channel CT volumes (the reference nets have in_channels=1)')
     wins = [(d0, h0, w0) for d0 in window_starts(D, window[0], stride[0]) for h0 in window_starts(H, window[1], stride[1])
             for w0 in window_starts(W, window[2], stride[2])]
-    overlap = any(s < w and L > w for s, w, L in zip(stride, window, (D, H, W)))
+    # windows overlap when the stride is smaller than the window OR when the last window of an axis is clamped to the volume edge
+    # (L not a multiple of the stride): either way the stitched value is the mean over the covering windows
+    overlap = any(b - a < w for L, w, s in zip((D, H, W), window, stride) for a, b in zip(window_starts(L, w, s), window_starts(L, w, s)[1:]))
     if distributed is None:
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     mine = [wins[i] for i in shard_indices(len(wins))] if distributed else wins
