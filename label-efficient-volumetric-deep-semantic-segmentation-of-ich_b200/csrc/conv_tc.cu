@@ -97,7 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_bytes;
           if (elect_one()) {
-            if (p.dbg & 2) { mbar_arrive(&full_bar[stage]); }
+            if (ICH_DBG(p) & 2) { mbar_arrive(&full_bar[stage]); }
             else {
               mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
               tma_load_4d(sa, &map_x, &full_bar[stage], kc * p.cw, w0 - KS / 2, h0 - KS / 2, n * p.D + d - planes_lo);
@@ -148,7 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
           uint32_t accum = (kc == 0) ? 0u : 1u;
           uint32_t a_kd = a_lo0;
           if (KS == 1) {
-            if (!(p.dbg & 1)) {
+            if (!(ICH_DBG(p) & 1)) {
               for (uint32_t ks = 0; ks < ((uint32_t)p.cw >> 4); ++ks) {
                 const uint64_t bdesc = pack64(b_lo + 2u * ks, wide_hi);
                 uint32_t a_lo = a_lo0 + 2u * ks + (uint32_t)ii * tile16;
@@ -163,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
               }
             }
           } else
-          for (int kd = kd_lo; kd <= kd_hi && !(p.dbg & 1); ++kd, a_kd += plane16) {
+          for (int kd = kd_lo; kd <= kd_hi && !(ICH_DBG(p) & 1); ++kd, a_kd += plane16) {
             uint32_t a_kh = a_kd;
 #pragma unroll
             for (int kh = 0; kh < KS; ++kh, a_kh += row16) {
@@ -240,7 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
               const int ti = (int)(tap >> 2), tj = (int)(tap >> 1) & 1, tl = (int)tap & 1;
               yrow = p.y + (fine0 + ti * fine_i + tj * fine_j + tl) * p.y_ld + bias0;
             }
-            if (valid && !(p.dbg & 4)) {
+            if (valid && !(ICH_DBG(p) & 4)) {
               float f32[16];
               float bv[16];
               if (p.bias) {       // 16 consecutive, 64-byte aligned bias values
@@ -586,7 +586,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes + p.a_off;
         uint8_t* sb = smem + (size_t)stage * p.stage_bytes + p.b_off;
-        if (p.dbg & 2) { if (elect_one()) mbar_arrive(&full_bar[stage]); }
+        if (ICH_DBG(p) & 2) { if (elect_one()) mbar_arrive(&full_bar[stage]); }
         else if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
           for (int pl = 0; pl < p.KD; ++pl) {
@@ -638,7 +638,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           uint32_t bk_row = (((st + p.b_off) & 0x3FFFFu) >> 4) | (KU << 16);       // LBO = one position
           const uint32_t BW = KU * (uint32_t)(p.WB + 2);                           // dy row pitch in 16-byte units
           const bool mine = ii < khn;                                              // kh-split: a single accumulator (issuer 0)
-          for (int r = 0; r < p.R && !(p.dbg & 1) && mine; ++r, a_row += PW, bk_row += BW) {
+          for (int r = 0; r < p.R && !(ICH_DBG(p) & 1) && mine; ++r, a_row += PW, bk_row += BW) {
             for (uint32_t s = 0; s < (uint32_t)p.WB; s += 16) {                    // 16 positions per MMA
               const uint64_t bdesc = pack64(bk_row + KU * s, kb_hi);
               const uint32_t a_kh = a_row + AU * s + AU + (uint32_t)ii * PW;       // x position q = s (skip the halo column), kernel row ii
@@ -647,7 +647,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             }
           }
         } else
-        for (int r = 0; r < p.R && !(p.dbg & 1); ++r, a_row += PW, b_row += WB) {
+        for (int r = 0; r < p.R && !(ICH_DBG(p) & 1); ++r, a_row += PW, b_row += WB) {
           for (uint32_t s = 0; s < (uint32_t)p.WB; s += 16) {                      // 16 positions per MMA
             const uint64_t bdesc = pack64(b_row + BU * s, b_hi);
             const uint32_t a_s = a_row + AU * s;

@@ -128,7 +128,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + p.a_bytes;
           if (elect_one()) {
-            if (p.dbg & 2) mbar_arrive(&full_bar[stage]);
+            if (ICH_DBG(p) & 2) mbar_arrive(&full_bar[stage]);
             else {
               mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + (p.b_resident ? 0u : p.b_bytes));
               tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + pl);
@@ -197,7 +197,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             const uint32_t b_addr = p.b_resident ? (w_base + (uint32_t)kc * p.b_bytes) : (sa + p.a_bytes);
             uint32_t b_tap = ((b_addr & 0x3FFFFu) >> 4) | (1u << 16);
             uint32_t a_kh = a_lo0;
-            if (!(p.dbg & 1)) {
+            if (!(ICH_DBG(p) & 1)) {
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
 #pragma unroll
@@ -252,7 +252,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       for (int k = 0; k < SNB; ++k) csum[k] = csq[k] = 0.f;
     }
     const int n0 = nb_fixed * p.NB;
-    const bool plain = !(p.dbg & 4);
+    const bool plain = !(ICH_DBG(p) & 4);
     // 16 accumulator columns -> bias / ReLU -> bf16 (-> statistics of the stored values) -> two 16-byte stores
     auto emit16 = [&](const uint32_t* v, const int c0, bf16* yrow) __attribute__((always_inline)) {
       uint32_t pk[8];

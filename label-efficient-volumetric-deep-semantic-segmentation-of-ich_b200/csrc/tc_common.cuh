@@ -5,6 +5,14 @@
 #include <mutex>
 #include <stdlib.h>
 
+// Ablation switches (ICH_TC_DBG: no MMA issue / no TMA loads / no epilogue stores) exist only in builds made with -DICH_TC_DEBUG
+// (profiling experiments, profiles/r01_ablations.txt); the production build compiles them out.
+#ifdef ICH_TC_DEBUG
+#define ICH_DBG(p) ((p).dbg)
+#else
+#define ICH_DBG(p) 0
+#endif
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------------- PTX wrappers

@@ -596,7 +596,10 @@ def test_graphed_training_step_matches_eager():
             for mode in ('eager', 'graph'):
                 torch.manual_seed(0)
                 net = UNet(**kw).to(DEV).train()
-                opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9) if optim_name == 'sgd' else torch.optim.Adam(net.parameters(), lr=1e-3)
+                # SGD with a tiny step keeps the six steps in the linear regime (the ComboLoss gradients are huge: BCE is summed over voxels), so
+                # replay and eager can be compared through the parameter UPDATES; Adam exercises the capturable optimizer path
+                opt = torch.optim.SGD(net.parameters(), lr=1e-7) if optim_name == 'sgd' else torch.optim.Adam(net.parameters(), lr=1e-4)
+                p0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
                 lossf = ComboLoss(alpha=0.5, beta=0.5, reduction='mean', p=1)
 
                 def train_step(x, m):
@@ -612,15 +615,20 @@ def test_graphed_training_step_matches_eager():
                 net.eval()
                 with torch.no_grad():
                     ev = net(xs[0]).cpu()
-                results[optim_name, mode] = (losses, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, ev)
+                results[optim_name, mode] = (losses, {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, ev, p0)
     for optim_name in ('sgd', 'adam'):
-        (le, pe, ee), (lg, pg, eg) = results[optim_name, 'eager'], results[optim_name, 'graph']
-        assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(le, lg)), (optim_name, le, lg)
+        (le, pe, ee, p0), (lg, pg, eg, _) = results[optim_name, 'eager'], results[optim_name, 'graph']
+        assert all(abs(a - b) <= 5e-3 * abs(a) for a, b in zip(le, lg)), (optim_name, le, lg)
         assert rel(eg, ee) < 2e-2
+        moved = 0
         for k, v in pe.items():
             if not v.is_floating_point():
                 assert torch.equal(pg[k], v), k                           # num_batches_tracked advanced inside the graph too
-            elif optim_name == 'sgd':
-                # SGD is linear in the gradients: replay and eager differ only by the summation order of the fp32 atomics.  (Adam divides
-                # by sqrt(v): near-zero gradients flip the sign of whole updates, so its parameters are compared through the losses only.)
-                assert (pg[k] - v).abs().max().item() <= 1e-3 * (v.abs().max().item() + 1e-3), k
+            elif optim_name == 'sgd' and 'running' not in k:
+                du_e, du_g = v - p0[k], pg[k] - p0[k]                     # what six steps did to the parameter, eager vs replay
+                if du_e.abs().max() > 0:
+                    moved += 1
+                    assert (du_g - du_e).norm().item() <= 2e-2 * du_e.norm().item() + 1e-9, k
+            elif 'running' in k:
+                assert rel(pg[k], v) < 1e-3, k                            # BatchNorm running statistics updated inside the graph
+        assert optim_name != 'sgd' or moved > 20
