@@ -181,8 +181,9 @@ class Job:
             self.lossf = getattr(losses, wl['loss'])(**wl['loss_kw'])
             self.host = [pin(torch.rand(*shape, generator=g)), pin((torch.rand(*shape, generator=g) > 0.98).float())]
         elif self.kind == 'nce_global':
-            self.lossf = losses.InfoNCELoss(set_size=batch * (world if os.environ.get('ICH_B200_GLOBAL_NCE') == '1' and arm == 'b200' else 1),
-                                            tau=0.1, device=str(dev))
+            # set_size = the LOCAL batch (what the module checks against); with ICH_B200_GLOBAL_NCE=1 the drop-in's loss gathers the
+            # embeddings of all ranks itself (ops.gather_rows)
+            self.lossf = losses.InfoNCELoss(set_size=batch, tau=0.1, device=str(dev))
             self.host = [pin(torch.rand(*shape, generator=g)), pin(torch.rand(*shape, generator=g))]
             self.units *= 2
         elif self.kind == 'nce_local':
@@ -491,4 +492,10 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    try:
+        main()
+    except BaseException:       # noqa: BLE001 -- print, then leave without NCCL / CUDA teardown (a rank that dies in a collective job must not hang the others)
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)

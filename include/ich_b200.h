@@ -54,6 +54,9 @@ int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD,
 /* which kernel (and therefore which weight pack) a shape uses: 0 none, 1 slab kernel ([kd][kh][kw][Cout][Cin]),
  * 2 plane-streaming kernel with the depth taps folded into the MMA N dimension ([kh][kw][2-kd][Cout][Cin])            */
 int ich_conv_tc_variant(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW);
+/* host-only: the tiling the slab kernel picks for a shape -- out[0..9] = cout block, rows per slab, M tiles per item, accumulator sets,
+ * pipeline stages, kd-split, dynamic shared memory bytes, TMEM columns, K chunk width, work items; returns non-zero if unsupported */
+int ich_conv_tc_plan_info(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, long long* out);
 int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
                     int Cin, int Cout, int KD, int KH, int KW, int relu, void* stream);
 /* same, with the BatchNorm batch statistics (fp64 per-channel sum / sum of squares of the stored outputs) fused into the epilogue */

@@ -35,6 +35,9 @@ struct Params {
   int y32;   // output rows are 32-byte aligned: 256-bit stores
   int cw;    // channels per K chunk: 16 (32-byte swizzled rows) for the 3x3 kernels; 16 / 32 / 64 (32 / 64 / 128-byte rows) for the 1x1
              // GEMMs (transposed conv, heads), whose stages are small and whose TMA loads were bound by the number of 32-byte requests
+  int kds;   // kd-split (3-D layers with Cout % 128 == 0): a pipeline stage holds ONE input plane and the 9 taps of ONE depth tap, so that
+             // a 128-wide cout block fits (9 x 128 x 32 B = 36 KB of weights per stage instead of 27 x 64 x 32 B = 55 KB): N = 128 MMAs
+             // run at the full tensor rate (64 cycles) where N = 64 ones are operand-fetch bound (48 cycles for half the work)
 };
 
 constexpr int STAGES = 2;        // weight-gradient kernel
@@ -43,30 +46,31 @@ constexpr int MAX_STAGES = 8;    // forward kernel: runtime depth (2 for the big
 // BatchNorm statistics are fused (128 statistic registers per thread), eight otherwise (two per TMEM lane quadrant, each taking half of
 // the accumulator columns): the transposed-conv scatter epilogue (16 column chunks per tile) was bound by its four warps.
 constexpr int F_ISSUERS = 2;
-template <bool STATS> __host__ __device__ constexpr int f_epi_warps() { return STATS ? 4 : 8; }
-template <bool STATS> __host__ __device__ constexpr int f_threads() { return 32 * (4 + f_epi_warps<STATS>()); }
+// WIDE = cout blocks of 128 with fused statistics: eight epilogue warps there too, each set keeping the statistics of its 64 columns
+template <bool STATS, bool WIDE = false> __host__ __device__ constexpr int f_epi_warps() { return (STATS && !WIDE) ? 4 : 8; }
+template <bool STATS, bool WIDE = false> __host__ __device__ constexpr int f_threads() { return 32 * (4 + f_epi_warps<STATS, WIDE>()); }
 constexpr int W_THREADS = 256;   // weight-gradient kernel: warp 0 TMA, warps 1 / 6 / 7 MMA issuers (one per accumulator group), warps 2..5 epilogue
 constexpr int W_ISSUERS = 3;
 
-template <int KS, bool STATS>
-__global__ void __launch_bounds__(f_threads<STATS>(), 1)
+template <int KS, bool STATS, bool WIDE = false>
+__global__ void __launch_bounds__(f_threads<STATS, WIDE>(), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage0 A|B][stage1 A|B] ... then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_stat[2][64];          // per-CTA BatchNorm partial sums (one global atomic per channel per CTA)
+  __shared__ float s_stat[2][128];         // per-CTA BatchNorm partial sums (one global atomic per channel per CTA)
 
   // broadcast from lane 0 so the compiler KNOWS the role index is warp-uniform (uniform branches + uniform datapath)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  if (STATS && threadIdx.x < 128) s_stat[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
+  if (STATS && threadIdx.x < 256) s_stat[threadIdx.x >> 7][threadIdx.x & 127] = 0.f;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], F_ISSUERS); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], F_ISSUERS); mbar_init(&tempty_bar[a], f_epi_warps<STATS>()); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], F_ISSUERS); mbar_init(&tempty_bar[a], f_epi_warps<STATS, WIDE>()); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -92,20 +96,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int rb = (int)(t % p.n_rb); t /= p.n_rb;
         const int d = (int)(t % p.D); const int n = (int)(t / p.D);
         const int w0 = wb * p.WB, h0 = rb * p.R;
+        // kd-split: one stage per (channel chunk, depth tap) -- the slab box is ONE plane, the weight box the 9 taps of that depth tap;
+        // planes outside the volume are skipped (the issuers skip the same stages)
+        const int nsub = p.kds ? 3 : 1;
         for (int kc = 0; kc < p.KC; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-          uint8_t* sb = sa + p.a_bytes;
-          if (elect_one()) {
-            if (ICH_DBG(p) & 2) { mbar_arrive(&full_bar[stage]); }
-            else {
-              mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
-              tma_load_4d(sa, &map_x, &full_bar[stage], kc * p.cw, w0 - KS / 2, h0 - KS / 2, n * p.D + d - planes_lo);
-              tma_load_3d(sb, &map_w, &full_bar[stage], kc * p.cw, nb * p.NB, 0);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const int dd = p.kds ? d + sub - 1 : d - planes_lo;
+            if (p.kds && (dd < 0 || dd >= p.D)) continue;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+            uint8_t* sb = sa + p.a_bytes;
+            if (elect_one()) {
+              if (ICH_DBG(p) & 2) { mbar_arrive(&full_bar[stage]); }
+              else {
+                mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
+                tma_load_4d(sa, &map_x, &full_bar[stage], kc * p.cw, w0 - KS / 2, h0 - KS / 2, n * p.D + dd);
+                tma_load_3d(sb, &map_w, &full_bar[stage], kc * p.cw, nb * p.NB, p.kds ? sub * 9 : 0);
+              }
             }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -132,20 +143,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
       for (long long sp = s_begin; sp < n_spatial; sp += s_step, ++it) {
         long long t = sp / p.n_wb / p.n_rb;
         const int d = (int)(t % p.D);
-        const int kd_lo = (p.KD == 3 && d == 0) ? 1 : 0;
-        const int kd_hi = (p.KD == 3) ? ((d == p.D - 1) ? 1 : 2) : 0;
+        // kd-split: the depth taps are separate pipeline stages of ONE plane each (sub-stages below), not planes of one slab
+        const int kd_lo = (p.KD == 3 && !p.kds && d == 0) ? 1 : 0;
+        const int kd_hi = (p.KD == 3 && !p.kds) ? ((d == p.D - 1) ? 1 : 2) : 0;
+        const int nsub = p.kds ? 3 : 1;
+        bool first_stage = true;
         const int acc = (p.nacc == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (p.nacc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T) * NB;
-        for (int kc = 0; kc < p.KC; ++kc) {
+        for (int kc = 0; kc < p.KC; ++kc)
+        for (int sub = 0; sub < nsub; ++sub) {
+          if (p.kds && (d + sub - 1 < 0 || d + sub - 1 >= p.D)) continue;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t a_lo0 = (((sa & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)kd_lo * plane16;
           uint32_t b_lo = ((((sa + p.a_bytes) & 0x3FFFFu) >> 4) | (1u << 16)) + (uint32_t)(kd_lo * KS * KS) * btap16;
-          uint32_t accum = (kc == 0) ? 0u : 1u;
+          uint32_t accum = first_stage ? 0u : 1u;
+          first_stage = false;
           uint32_t a_kd = a_lo0;
           if (KS == 1) {
             if (!(ICH_DBG(p) & 1)) {
@@ -197,8 +214,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int q = warp & 3;
     const int l = q * 32 + lane;
     const int eset = (warp - 4) >> 2;
-    const int c_lo = (f_epi_warps<STATS>() == 8 && p.NB >= 32) ? eset * (p.NB / 32) * 16 : 0;
-    const int c_hi = (f_epi_warps<STATS>() == 8 && p.NB >= 32) ? (eset == 0 ? (p.NB / 32) * 16 : p.NB) : (eset == 0 ? p.NB : 0);
+    const int c_lo = (f_epi_warps<STATS, WIDE>() == 8 && p.NB >= 32) ? eset * (p.NB / 32) * 16 : 0;
+    const int c_hi = (f_epi_warps<STATS, WIDE>() == 8 && p.NB >= 32) ? (eset == 0 ? (p.NB / 32) * 16 : p.NB) : (eset == 0 ? p.NB : 0);
     uint32_t it = 0;
     float csum[STATS ? 64 : 1], csq[STATS ? 64 : 1];
     if (STATS) {
@@ -228,7 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int fine_i = 4 * p.H * p.W, fine_j = 2 * p.W;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * p.T + tt) * p.NB);
 #pragma unroll
-        for (int c0 = 0; c0 < (KS == 1 ? 256 : 64); c0 += 16) {
+        for (int c0 = 0; c0 < (KS == 1 ? 256 : 128); c0 += 16) {
           if (c0 >= c_lo && c0 < c_hi) {
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)c0, v);
@@ -256,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (p.bias) a += bv[k];
                 if (p.relu) a = fmaxf(a, 0.f);
                 f32[k] = a;
-                if (STATS && c0 < 64) {   // statistics of the value as stored (bf16-rounded)
+                if (STATS && (WIDE || c0 < 64)) {   // statistics of the value as stored (bf16-rounded); WIDE: this warp set's 64 columns
                   const float rv = __bfloat162float(__float2bfloat16_rn(a));
                   csum[(c0 + k) & 63] += rv;
                   csq[(c0 + k) & 63] = fmaf(rv, rv, csq[(c0 + k) & 63]);
@@ -278,9 +295,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
       for (int k = 0; k < 64; ++k) {
         const float a = warp_sum(csum[k]), b = warp_sum(csq[k]);
-        if (lane == 0) { atomicAdd(&s_stat[0][k], a); atomicAdd(&s_stat[1][k], b); }
+        if (lane == 0) { atomicAdd(&s_stat[0][(WIDE ? c_lo : 0) + k], a); atomicAdd(&s_stat[1][(WIDE ? c_lo : 0) + k], b); }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * f_epi_warps<STATS, WIDE>()) : "memory");
       if (warp == 4) {
         for (int k = lane; k < p.NB; k += 32) {
           atomicAdd(&p.stat_sum[nb_fixed * p.NB + k], (double)s_stat[0][k]);
@@ -327,11 +344,18 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   int bestR = 0, bestT = 0, bestAcc = 0, bestNB = 0, bestStages = 0;
   size_t best_smem = 0;
   uint32_t best_a = 0;
-  // cout block: <= 64 for the 3x3 kernels (27 taps of weights share the stage), up to 256 for 1x1 GEMMs where a larger N
-  // amortises the per-MMA operand fetch (~76 cycles per MMA measured for any N <= 64, scratch/mma_rate.cu)
-  for (int NB = (KS == 1 ? 256 : 64); NB >= 16; NB -= 16) {
+  // cout block: <= 64 for the 3x3x3 kernels whose stage holds all 27 taps, 128 when a stage holds 9 taps (2-D layers, and 3-D layers in
+  // kd-split mode: one plane + one depth tap per stage) -- an N = 128 MMA runs at the full tensor rate (64 cycles), an N = 64 one is
+  // operand-fetch bound (48 cycles for half the work, profiles/r01_mma_rate2.txt); up to 256 for 1x1 GEMMs
+  static int wide_env = -1;
+  if (wide_env < 0) { const char* e = getenv("ICH_TC_NB128"); wide_env = e ? atoi(e) : 1; }
+  const bool wide = KS == 3 && wide_env && Cout % 128 == 0;
+  const int kds = (wide && KD == 3) ? 1 : 0;
+  const int stage_taps = kds ? 9 : taps, stage_planes = kds ? 1 : KD;
+  for (int NB = (KS == 1 ? 256 : (wide ? 128 : 64)); NB >= 16; NB -= 16) {
     if (Cout % NB || (nb_must_divide && nb_must_divide % NB)) continue;
-    const uint32_t b_bytes = (uint32_t)taps * NB * rowb;
+    if (KS == 3 && NB > 64 && NB != 128) continue;              // 3x3 epilogues: column halves of 64 (statistics) -> 128 or <= 64
+    const uint32_t b_bytes = (uint32_t)stage_taps * NB * rowb;
     for (int R = 1; R <= H && R <= 64; ++R) {
       const int RB = R + 2 * hw;
       const int T = row_mode ? R : (((R - 1) * PW + WB) + 127) / 128;
@@ -339,14 +363,14 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
       if (2 * T * NB <= 512) nacc = 2;
       else if (T * NB <= 512) nacc = 1;
       else continue;
-      uint32_t a_bytes = (uint32_t)KD * RB * PW * rowb;
+      uint32_t a_bytes = (uint32_t)stage_planes * RB * PW * rowb;
       a_bytes = cw > 16 ? ((a_bytes + 1023u) & ~1023u) : ((a_bytes + 127u) & ~127u);     // the weight tile follows: keep wide-swizzle tiles 1024-aligned
       long long over = row_mode ? 0 : ((long long)(128 * T + 2 * hw * PW + 2 * hw) - (long long)RB * PW) * (long long)rowb;
       if (over < 0) over = 0;
       size_t stage = ((size_t)a_bytes + b_bytes + 1023) & ~(size_t)1023;
       int stages = (int)((SMEM_LIMIT - (size_t)over - 1024) / stage);
       if (stages > MAX_STAGES) stages = MAX_STAGES;
-      if (KS == 3 && stages > 3) stages = 3;
+      if (KS == 3 && stages > (kds ? 4 : 3)) stages = kds ? 4 : 3;
       if (stages < 2) continue;
       size_t total = (size_t)stages * stage + (size_t)over + 1024;   // +1024: manual alignment of the dynamic base
       long long blocks = (H + R - 1) / R;
@@ -361,7 +385,7 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
     if (KS == 3 && best_cost >= 0) break;    // 3x3: take the largest feasible cout block (fewest slab re-reads)
   }
   const int NB = bestNB;
-  const uint32_t b_bytes = (uint32_t)taps * NB * rowb;
+  const uint32_t b_bytes = (uint32_t)stage_taps * NB * rowb;
   if (best_cost < 0) return pl;
   Params& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
@@ -370,7 +394,8 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / cw; p.taps = taps; p.cw = cw;
   p.nacc = bestAcc; p.stages = bestStages;
   p.a_bytes = best_a;
-  p.a_tx_bytes = (uint32_t)KD * p.RB * PW * rowb;
+  p.a_tx_bytes = (uint32_t)stage_planes * p.RB * PW * rowb;
+  p.kds = kds;
   p.b_bytes = b_bytes;
   p.stage_bytes = (uint32_t)(((size_t)best_a + b_bytes + 1023) & ~(size_t)1023);
   uint32_t cols = 32;
@@ -404,6 +429,17 @@ int ich_conv_tc_supported(int N, int D, int H, int W, int Cin, int Cout, int KD,
   return make_plan(N, D, H, W, Cin, Cout, KD, KH, KW).ok ? 1 : 0;
 }
 
+// Host-only: the tiling the slab kernel would use for a shape (no driver needed, so the planner is testable without a GPU).
+// out[0..9] = NB, R, T, accumulator sets, pipeline stages, kd-split, dynamic shared memory bytes, TMEM columns, K chunk width, work items.
+int ich_conv_tc_plan_info(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, long long* out) {
+  Plan pl = make_plan(N, D, H, W, Cin, Cout, KD, KH, KW);
+  if (!pl.ok) return 1;
+  const Params& p = pl.p;
+  out[0] = p.NB; out[1] = p.R; out[2] = p.T; out[3] = p.nacc; out[4] = p.stages; out[5] = p.kds; out[6] = (long long)pl.smem_bytes;
+  out[7] = p.tmem_cols; out[8] = p.cw; out[9] = p.n_items;
+  return 0;
+}
+
 static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int relu,
                           cudaStream_t stream, const char* what, double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
   Params& p = pl.p;
@@ -428,7 +464,7 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
     // x as (C, W, H, N*D): the box lands as [plane][row][pos][16 ch] = 32-byte rows, 32B-swizzled (full 32 B L2 sectors)
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
     cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2};
-    cuuint32_t box[4] = {(cuuint32_t)p.cw, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)KD};
+    cuuint32_t box[4] = {(cuuint32_t)p.cw, (cuuint32_t)p.PW, (cuuint32_t)p.RB, (cuuint32_t)(p.kds ? 1 : KD)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      p.cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : p.cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
@@ -439,7 +475,7 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
     // w [taps][Cout][Cin] as (Cin, Cout, taps): box = [tap][NB rows][16 ch], same 32-byte swizzled rows
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)p.taps};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-    cuuint32_t box[3] = {(cuuint32_t)p.cw, (cuuint32_t)p.NB, (cuuint32_t)p.taps};
+    cuuint32_t box[3] = {(cuuint32_t)p.cw, (cuuint32_t)p.NB, (cuuint32_t)(p.kds ? 9 : p.taps)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -453,6 +489,7 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_LIMIT));
     if (e != cudaSuccess) cudaGetLastError();
     ICH_REQUIRE(e == cudaSuccess, "%s: cannot raise dynamic shared memory: %s", what, cudaGetErrorString(e));
@@ -461,7 +498,8 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
   grid = grid / p.n_nb * p.n_nb;             // every CTA owns one cout block; n_items is a multiple of n_nb
   if (grid < p.n_nb) grid = p.n_nb;
-  if (p.KS == 3 && stat_sum) conv_tc_kernel<3, true><<<(unsigned)grid, f_threads<true>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
+  if (p.KS == 3 && stat_sum && p.NB == 128) conv_tc_kernel<3, true, true><<<(unsigned)grid, f_threads<true, true>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
+  else if (p.KS == 3 && stat_sum) conv_tc_kernel<3, true><<<(unsigned)grid, f_threads<true>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
   else if (p.KS == 3) conv_tc_kernel<3, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
   else conv_tc_kernel<1, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
   return ich_check_launch(what);

@@ -63,7 +63,7 @@ def test_conv_fwd_dgrad_wgrad(case, prec):
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16'])
 @pytest.mark.parametrize('training', [True, False])
-@pytest.mark.parametrize('chan', [(8, 16), (16, 32), (32, 128)])   # the last two run the tcgen05 conv with fused BN statistics in bf16 mode
+@pytest.mark.parametrize('chan', [(8, 16), (16, 32), (32, 128), (64, 256)])   # all but the first run the tcgen05 conv with fused BN statistics in bf16 mode (128 / 256: cout blocks of 128, kd-split)
 def test_conv_bn_relu_unit(prec, training, chan):
     g = torch.Generator().manual_seed(3)
     cin, cout = chan
@@ -776,6 +776,12 @@ TC_CASES = [  # N, D, H, W, Cin, Cout, k3d  -- shapes the tcgen05 kernel must ta
     (2, 1, 32, 128, 32, 32, False),     # 2-D wgrad kw-fold (KD = 1)
     (1, 2, 6, 48, 64, 64, True),        # kw-fold + kh-split on 48-wide rows (one w-block of 48, column halo inside the TMA box)
     (1, 1, 24, 64, 16, 32, False),      # 2-D, Cin = 16: kw-fold with 16-channel x blocks (32-byte rows)
+    (1, 4, 16, 32, 64, 128, True),      # kd-split slab kernel: cout block of 128 (N = 128 MMAs), one plane + one depth tap per stage
+    (2, 2, 8, 16, 128, 256, True),      # kd-split, two cout blocks of 128, D = 2 (every item skips one of the three depth taps); dgrad 256 -> 128
+    (1, 1, 16, 16, 256, 128, True),     # kd-split with D = 1: only the centre depth tap is ever staged
+    (2, 1, 32, 64, 64, 128, False),     # 2-D with a 128-wide cout block (9 taps per stage as before, N = 128)
+    (1, 1, 24, 128, 128, 256, False),   # 2-D row mode, two cout blocks of 128; data-gradient 256 -> 128
+    (1, 3, 20, 32, 128, 128, True),     # kd-split, several items per CTA, H not a multiple of the row block
 ]
 
 
@@ -898,6 +904,8 @@ FULL_SIZE = [  # BASELINE cfg-3 layer shapes (per-GPU batch 8): N, D, H, W, Cin,
     (8, 64, 128, 128, 1, 16),      # d0.c1: first layer, tcgen05 im2col kernels (forward + weight gradient)
     (4, 64, 128, 128, 64, 32),     # u2.c1 (half batch): two Cin blocks in the kw-fold wgrad, KC = 4 in the streaming kernel
     (8, 16, 32, 32, 64, 128),      # d2.c2: wgrad kh-split with N = 128 (128-byte dy rows, two blocks)
+    (8, 16, 32, 32, 256, 128),     # u0.c1: kd-split slab kernel with a 128-wide cout block (forward) and two of them (data-gradient 128 -> 256)
+    (8, 8, 16, 16, 128, 256),      # bt.c2: kd-split, deepest level
 ]
 
 

@@ -620,15 +620,53 @@ def test_graphed_training_step_matches_eager():
         (le, pe, ee, p0), (lg, pg, eg, _) = results[optim_name, 'eager'], results[optim_name, 'graph']
         assert all(abs(a - b) <= 5e-3 * abs(a) for a, b in zip(le, lg)), (optim_name, le, lg)
         assert rel(eg, ee) < 2e-2
-        moved = 0
+        moved, num, den = 0, 0.0, 0.0
         for k, v in pe.items():
             if not v.is_floating_point():
                 assert torch.equal(pg[k], v), k                           # num_batches_tracked advanced inside the graph too
             elif optim_name == 'sgd' and 'running' not in k:
-                du_e, du_g = v - p0[k], pg[k] - p0[k]                     # what six steps did to the parameter, eager vs replay
+                du_e, du_g = (v - p0[k]).double(), (pg[k] - p0[k]).double()    # what six steps did to the parameter, eager vs replay
                 if du_e.abs().max() > 0:
                     moved += 1
-                    assert (du_g - du_e).norm().item() <= 2e-2 * du_e.norm().item() + 1e-9, k
+                    num += (du_g - du_e).pow(2).sum().item()
+                    den += du_e.pow(2).sum().item()
+                    # per tensor: loose (a first-layer gradient is a heavily cancelling sum over 2 M voxels accumulated with fp32 atomics)
+                    assert (du_g - du_e).norm().item() <= 0.25 * du_e.norm().item() + 1e-9, k
             elif 'running' in k:
                 assert rel(pg[k], v) < 1e-3, k                            # BatchNorm running statistics updated inside the graph
-        assert optim_name != 'sgd' or moved > 20
+        if optim_name == 'sgd':
+            assert moved > 20 and num ** 0.5 <= 2e-2 * den ** 0.5, (moved, num, den)      # all updates together: replay == eager to 2 %
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Drop-in boundary: the reference's REAL trainer (models/optim/UNet2D.py, unmodified, from baseline/_ref) runs its
+# own train() / evaluate() loops on top of the drop-in modules
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'code')), reason='needs baseline/_ref (made by __graft_entry__.build() '
+                    'where the reference tree exists; it travels to the GPU box with the snapshot)')
+def test_reference_trainer_on_the_drop_in(tmp_path):
+    import subprocess
+    import sys
+    from src.models.networks.UNet import UNet
+    torch.manual_seed(0)
+    init = UNet(depth=3, use_3D=False, in_channels=1, out_channels=1, top_filter=16, midchannels_factor=1, p_dropout=0.0).state_dict()
+    torch.save(init, tmp_path / 'init.pt')
+    driver = os.path.join(ROOT, 'tests', 'ref_trainer_driver.py')
+    runs = {}
+    for name, mode, device, prec in (('reference', 'reference', 'cpu', ''), ('dropin_fp32', 'dropin', 'cuda', 'fp32'), ('dropin_bf16', 'dropin', 'cuda', 'bf16')):
+        env = dict(os.environ, ICH_B200_PRECISION=prec) if prec else dict(os.environ)
+        r = subprocess.run([sys.executable, driver, mode, device, str(tmp_path / 'init.pt'), str(tmp_path / f'{name}.json')], capture_output=True, text=True,
+                           env=env, timeout=900)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        runs[name] = json.load(open(tmp_path / f'{name}.json'))
+    ref, f32, b16 = runs['reference'], runs['dropin_fp32'], runs['dropin_bf16']
+    diag('reference_trainer', {k: {'loss': [e[1] for e in v['evolution']], 'valid_dice': [e[2] for e in v['evolution']], 'dice': v['dice']} for k, v in runs.items()})
+    assert f32['n_keys'] == ref['n_keys'] and f32['ckpt_keys'] == ref['ckpt_keys'] and f32['ckpt_epochs'] == 10
+    # same trainer, same data order, same initial weights: the fp32 engine follows the reference's loss trajectory
+    assert abs(f32['evolution'][0][1] - ref['evolution'][0][1]) < 1e-3 * ref['evolution'][0][1]
+    for e_c, e_r in zip(f32['evolution'], ref['evolution']):
+        assert abs(e_c[1] - e_r[1]) < 1e-2 * e_r[1], (e_c, e_r)
+    assert abs(f32['dice']['all'] - ref['dice']['all']) < 2e-2
+    # bf16 engine: trains to the same quality
+    assert all(np.isfinite(e[1]) for e in b16['evolution']) and b16['evolution'][-1][1] < b16['evolution'][0][1]
+    assert abs(b16['dice']['all'] - ref['dice']['all']) < 5e-2
