@@ -379,7 +379,7 @@ def main():
     units_step = job.units if strong else world * job.units
 
     step_fn = job.step
-    if args.graph and args.impl == 'b200' and job.opt is not None:
+    if args.graph and args.impl == 'b200' and job.opt is not None and job.kind != 'nce_local':     # LocalInfoNCE draws its regions on the host every step
         from ich_b200.graph import GraphedStep
         step_fn = GraphedStep(job.step, job.opt, warmup=2)       # calls 1-2 eager, call 3 (still warm-up, >= 3 enforced above) captures
 
@@ -470,7 +470,7 @@ def main():
             'vs_baseline': None, 'dtype': ('bf16' if args.precision == 'bf16' else 'f32') if args.impl == 'b200' else ('bf16' if args.cudnn_mode == 'bf16' else 'tf32'),
             'data': 'synthetic', 'config': {'workload': wl['desc']},
             'run': {'global_batch': world * batch, 'parallelism': f'dp{world}' + (' (windows of one volume sharded, uint8 mask all-reduce)' if strong else ''),
-                    'cuda_graph': bool(args.graph),
+                    'cuda_graph': bool(getattr(step_fn, 'graph', None) is not None),
                     'l2': 'working set per step (GBs of activations) >> 126 MB L2, no flush needed'},
             'e2e': {'value': units_step * args.steps / t_e2e, 'unit': 'voxels/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h[0], 'ms_per_step': 1e3 * t_e2e / args.steps},

@@ -103,8 +103,60 @@ class ConvBlock(nn.Module):
         nn.Dropout (reference UNet.py:175-176) is fused into the second unit's BN-apply / BN-backward kernels (counter-based
         Philox mask, no mask tensor); being RNG-dependent it matches the reference statistically, not element-wise."""
         drop_p = float(self.dropout.p) if (self.dropout.p > 0.0 and self.training) else 0.0
+        if self._pad_mid(x):
+            return self._forward_cl_padded_mid(x, concat_c, drop_p)
         x = self._unit(x, self.conv1, self.bn1)
         return self._unit(x, self.conv2, self.bn2, concat_c, drop_p)
+
+    # ---- 8-channel mid tensors (top_filter = 16 nets with midchannels_factor = 2: BASELINE.json configs[0]) ------------------------------
+    # The tcgen05 kernels work on 16-channel K chunks / cout blocks; an 8-channel tensor between the two units of a block would send both
+    # full-resolution convs of that block to the CUDA-core kernels (measured: 9.1 of 10.2 ms per cfg-1 step).  Instead the block runs
+    # with its mid tensor zero-padded to 16 channels: unit 1 gets 8 extra all-zero filters (their BatchNorm output is exactly 0), unit 2
+    # gets 8 extra all-zero input channels.  The padding is built with differentiable torch ops on the (tiny) parameters, so autograd
+    # hands every parameter exactly its own slice of the gradient; the statistics of the real channels are untouched.
+    def _pad_mid(self, x):
+        mid = self.conv1.out_channels
+        return (_cfg.get('tensor_cores') and x.dtype == torch.bfloat16 and mid % 16 == 8 and self.conv2.out_channels % 16 == 0
+                and self.conv1.kernel_size[0] == 3 and (x.shape[-1] == 1 or x.shape[-1] % 16 == 0))
+
+    def _forward_cl_padded_mid(self, x, concat_c, drop_p):
+        import torch.nn.functional as F
+        c1, b1, c2, b2 = self.conv1, self.bn1, self.conv2, self.bn2
+        nd = c1.weight.dim()
+        if not (self.training or not b1.track_running_stats) and not concat_c and _cfg.get('fold_eval_bn') and not torch.is_grad_enabled():
+            # inference with BatchNorm folded into the convs (ops.folded_eval_unit): pad the FOLDED weights, cached on the folded tensors
+            def padded(conv, bn, pad_out):
+                w, b = ops.folded_eval_unit(conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+                cached = getattr(w, '_ich_padded', None)
+                if cached is None:
+                    cached = (F.pad(w, (0, 0) * (nd - 1) + (0, 8)), F.pad(b, (0, 8))) if pad_out else (F.pad(w, (0, 0) * (nd - 2) + (0, 8)), b)
+                    w._ich_padded = cached
+                return cached
+            w1, bias1 = padded(c1, b1, True)
+            w2, bias2 = padded(c2, b2, False)
+            return ops.conv_forward(ops.conv_forward(x, w1, bias1, relu=True), w2, bias2, relu=True)
+        w1 = F.pad(c1.weight, (0, 0) * (nd - 1) + (0, 8))                       # [mid + 8, Cin, k..]: 8 all-zero filters
+        w2 = F.pad(c2.weight, (0, 0) * (nd - 2) + (0, 8))                       # [Cout, mid + 8, k..]: 8 all-zero input channels
+        bias1 = F.pad(c1.bias, (0, 8)) if c1.bias is not None else None
+        gamma = F.pad(b1.weight, (0, 8), value=1.0) if b1.weight is not None else None
+        beta = F.pad(b1.bias, (0, 8)) if b1.bias is not None else None
+        training = self.training or not b1.track_running_stats
+        rm = F.pad(b1.running_mean, (0, 8)) if b1.running_mean is not None else None
+        rv = F.pad(b1.running_var, (0, 8), value=1.0) if b1.running_var is not None else None
+        z = ops.ConvBnRelu.apply(x, w1, bias1, gamma, beta, rm, rv, training, True, 0, 0.0)
+        if training and b1.track_running_stats:
+            with torch.no_grad():                                               # the kernel updated the padded copies in place
+                b1.running_mean.copy_(rm[:-8])
+                b1.running_var.copy_(rv[:-8])
+            _PENDING_NBT.append(b1.num_batches_tracked)
+        training2 = self.training or not b2.track_running_stats
+        out = ops.ConvBnRelu.apply(z, w2, c2.bias, b2.weight, b2.bias, b2.running_mean, b2.running_var, training2, True, concat_c, drop_p)
+        if concat_c:
+            out, buf = out
+            out._ich_concat_buf = buf
+        if training2 and b2.track_running_stats:
+            _PENDING_NBT.append(b2.num_batches_tracked)
+        return out
 
     def forward_cl_head(self, x, final_conv, act):
         """This block followed by the single-class head `final_conv` (+ Sigmoid if act == 1), with the second unit and the head fused

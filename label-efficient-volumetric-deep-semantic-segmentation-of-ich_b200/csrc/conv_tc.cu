@@ -349,7 +349,9 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   // operand-fetch bound (48 cycles for half the work, profiles/r01_mma_rate2.txt); up to 256 for 1x1 GEMMs
   static int wide_env = -1;
   if (wide_env < 0) { const char* e = getenv("ICH_TC_NB128"); wide_env = e ? atoi(e) : 1; }
-  const bool wide = KS == 3 && wide_env && Cout % 128 == 0;
+  // ... but not on the smallest planes (16 x 16 at the bottleneck of cfg-3): an item is then a single M tile and the 36 KB weight stage
+  // is re-fetched for 9 MMAs of work (measured: bt.c2 forward 0.051 -> 0.069 ms with the wide block)
+  const bool wide = KS == 3 && wide_env && Cout % 128 == 0 && (long long)H * W >= 1024;
   const int kds = (wide && KD == 3) ? 1 : 0;
   const int stage_taps = kds ? 9 : taps, stage_planes = kds ? 1 : KD;
   for (int NB = (KS == 1 ? 256 : (wide ? 128 : 64)); NB >= 16; NB -= 16) {

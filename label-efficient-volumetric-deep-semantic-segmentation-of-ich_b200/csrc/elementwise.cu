@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(256, 3) bn_head_fwd_rows_kernel(const T* __res
       for (int o = 1; o < groups; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
       if (r < M && gi == 0) {
         p += bias;
-        out[r] = act == 1 ? 1.f / (1.f + expf(-p)) : p;
+        out[r] = act == 1 ? 1.f / (1.f + expf(-p)) : p;      // full-precision exp: the fp32 verification mode must match torch.sigmoid to 1e-7
       }
     }
   }
@@ -992,20 +992,20 @@ __global__ void __launch_bounds__(256, U == 8 ? 2 : 3) bn_head_bwd_reduce_rows_k
   float gb = 0.f;
   const long long step = (long long)gridDim.x * rpb;
   for (long long r0 = (long long)blockIdx.x * rpb + threadIdx.x / groups; r0 < M; r0 += U * step) {
+    // every load of the iteration is issued before the first use (ncu on the first version: 12 long-scoreboard stalls per issue --
+    // d(logit) was computed inside the load loop, so the loads of row u + 1 waited for the scalar loads of row u)
     typename Raw16<T>::R raw[U];
-    float dl[U];
+    float dl[U], pl[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * step;
-      if (r < M) {
-        raw[u] = Raw16<T>::load(y + r * y_ld + c);
-        const float p = out[r], g = dout[r];
-        dl[u] = act == 1 ? g * p * (1.f - p) : g;
-      } else {               // masked row: dl = 0 contributes nothing to any sum
-        raw[u] = Raw16<T>::zero();
-        dl[u] = 0.f;
-      }
+      const bool ok = r < M;               // masked row: dout = 0 -> dl = 0 contributes nothing to any sum
+      raw[u] = ok ? Raw16<T>::load(y + r * y_ld + c) : Raw16<T>::zero();
+      pl[u] = ok ? out[r] : 0.f;
+      dl[u] = ok ? dout[r] : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) dl[u] = act == 1 ? dl[u] * pl[u] * (1.f - pl[u]) : dl[u];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float a[V];
@@ -1103,20 +1103,18 @@ __global__ void __launch_bounds__(256, U == 8 ? 2 : 3) bn_head_bwd_apply_rows_ke
   }
   const long long step = (long long)gridDim.x * rpb;
   for (long long r0 = (long long)blockIdx.x * rpb + threadIdx.x / groups; r0 < M; r0 += U * step) {
-    typename Raw16<T>::R raw[U];
-    float dl[U];
+    typename Raw16<T>::R raw[U];       // all loads of the iteration first, d(logit) afterwards (see the reduction kernel)
+    float dl[U], pl[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * step;
-      if (r < M) {
-        raw[u] = Raw16<T>::load(y + r * y_ld + c);
-        const float p = out[r], g = dout[r];
-        dl[u] = act == 1 ? g * p * (1.f - p) : g;
-      } else {
-        raw[u] = Raw16<T>::zero();
-        dl[u] = 0.f;
-      }
+      const bool ok = r < M;
+      raw[u] = ok ? Raw16<T>::load(y + r * y_ld + c) : Raw16<T>::zero();
+      pl[u] = ok ? out[r] : 0.f;
+      dl[u] = ok ? dout[r] : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) dl[u] = act == 1 ? dl[u] * pl[u] * (1.f - pl[u]) : dl[u];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long r = r0 + u * step;

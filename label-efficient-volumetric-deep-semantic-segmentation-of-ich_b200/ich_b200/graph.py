@@ -19,8 +19,11 @@ from . import _lib
 
 
 class GraphedStep:
-    def __init__(self, step_fn, optimizer=None, warmup=3):
+    def __init__(self, step_fn, optimizer=None, warmup=3, strict=True):
+        """strict=False: a step that cannot be captured keeps running eagerly (`failed` holds the reason) instead of raising."""
         self.step_fn = step_fn
+        self.strict = strict
+        self.failed = None
         self.warmup = max(1, int(warmup))
         self.calls = 0
         self.graph = None
@@ -40,19 +43,31 @@ class GraphedStep:
         for s, t in zip(self.static_in, inputs):
             s.copy_(t)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         before = _lib.launches()
-        with torch.cuda.graph(self.graph):
-            self.static_out = self.step_fn(*self.static_in)
+        try:
+            with torch.cuda.graph(graph):
+                self.static_out = self.step_fn(*self.static_in)
+        except Exception as e:      # noqa: BLE001 -- e.g. a host synchronisation inside the step (dropout seed, numpy-drawn region corners)
+            if self.strict:
+                raise
+            self.failed = repr(e)
+            torch.cuda.synchronize()
+            from . import ops
+            ops.invalidate_packs()          # pack refreshes recorded during the aborted capture never ran: re-derive on next use
+            return False
+        self.graph = graph
         self.kernels_per_replay = _lib.launches() - before
         torch.cuda.synchronize()
+        return True
 
     def __call__(self, *inputs):
         if self.graph is None:
-            if self.calls < self.warmup:
+            if self.calls < self.warmup or self.failed:
                 self.calls += 1
                 return self.step_fn(*inputs)
-            self._capture(inputs)          # capturing does not execute: fall through to the first replay on these inputs
+            if not self._capture(inputs):  # capturing does not execute: fall through to the first replay on these inputs
+                return self.step_fn(*inputs)
         for s, t in zip(self.static_in, inputs):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)

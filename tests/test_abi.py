@@ -134,3 +134,25 @@ for cls, kw in cases:
     outs = [subprocess.run([sys.executable, '-c', code, path], capture_output=True, text=True, check=True).stdout
             for path in ('/root/reference/code', os.path.join(PKG, 'code'))]
     assert outs[0] == outs[1] and outs[0].count('\n') == 4
+
+
+def test_slab_kernel_planner_limits():
+    """Host-only planner of the tcgen05 slab kernel (ich_conv_tc_plan_info, no driver needed): for every conv shape of the BASELINE
+    configs the tiling must respect the hardware limits -- 227 KB of shared memory, 512 TMEM columns, >= 2 pipeline stages -- and the
+    128-channel-multiple layers must get 128-wide cout blocks (3-D ones in kd-split mode)."""
+    l = _lib.lib()
+    shapes = []
+    for c, (d, h, w) in ((32, (64, 128, 128)), (64, (32, 64, 64)), (128, (16, 32, 32)), (256, (8, 16, 16))):      # cfg-3 levels
+        shapes += [(8, d, h, w, c, c, 3), (8, d, h, w, 2 * c, c, 3), (8, d, h, w, c // 2 if c > 32 else 16, c, 3), (8, d, h, w, c, 2 * c, 3)]
+    for c, s in ((32, 512), (64, 256), (128, 128), (256, 64), (512, 32)):                                       # cfg-2 levels (2-D)
+        shapes += [(32, 1, s, s, c, c, 1), (32, 1, s, s, 2 * c, c, 1), (32, 1, s, s, max(c // 2, 16), c, 1)]
+    for n, d, h, w, cin, cout, kd in shapes:
+        out = (ctypes.c_longlong * 10)()
+        rc = l.ich_conv_tc_plan_info(n, d, h, w, cin, cout, kd, 3, 3, ctypes.cast(out, ctypes.c_void_p))
+        assert rc == 0, (n, d, h, w, cin, cout, kd)
+        nb, r, t, nacc, stages, kds, smem, tmem, cw, items = list(out)
+        assert smem <= 227 * 1024 and tmem <= 512 and nacc * t * nb <= 512 and stages >= 2 and cout % nb == 0 and items > 0
+        if cout % 128 == 0 and h * w >= 1024:
+            assert nb == 128 and kds == (1 if kd == 3 else 0), (cin, cout, kd, nb, kds)
+        else:
+            assert nb <= 64 and kds == 0

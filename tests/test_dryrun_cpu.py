@@ -181,7 +181,9 @@ def test_weight_packs_refreshed_from_the_optimizer_hook(dry, monkeypatch):
     from src.models.optim.LossFunctions import ComboLoss
     monkeypatch.setattr(ops, '_REFRESH_ANY_DEVICE', True)
     x = torch.rand(1, 1, 8, 16, 16)
-    net = UNet(depth=3, use_3D=True, top_filter=16, midchannels_factor=2, p_dropout=0.0).train()
+    # (32 base filters: a 16-filter net with midchannels_factor = 2 pads its 8-channel mid tensor with per-step derived weights, see
+    # ConvBlock._forward_cl_padded_mid -- those are packed on use, outside the batched refresh)
+    net = UNet(depth=3, use_3D=True, top_filter=32, midchannels_factor=2, p_dropout=0.0).train()
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     ComboLoss()(net(x), torch.zeros_like(x)).backward()
     n_single = dry.trace.count('ich_permute5')                  # first use: one derivation per pack
@@ -331,3 +333,26 @@ def test_graphed_step_needs_fresh_optimizer():
     opt2.step()
     with pytest.raises(RuntimeError):
         GraphedStep(lambda x: x, opt2)
+
+
+def test_padded_mid_channels_plumbing(dry):
+    """top_filter = 16 nets with midchannels_factor = 2 (BASELINE.json configs[0]): the 8-channel mid tensor of the first block is carried
+    zero-padded to 16 channels (tcgen05 granularity); every parameter still receives a gradient of its own shape, running statistics
+    keep their 8 entries, eval + folding takes the padded folded weights."""
+    from src.models.networks.UNet import UNet
+    with config.override(precision='bf16'):
+        net = UNet(depth=3, use_3D=True, top_filter=16, midchannels_factor=2, p_dropout=0.0).train()
+        blk = net.down_block[0]
+        x = torch.rand(1, 1, 8, 16, 16)
+        assert blk._pad_mid(torch.empty(1, 8, 16, 16, 1, dtype=torch.bfloat16))
+        net(x).sum().backward()
+        _grads_ok(net)
+        assert blk.bn1.running_mean.shape == (8,) and blk.bn1.num_batches_tracked == 1 and blk.bn2.num_batches_tracked == 1
+        assert blk.conv1.weight.grad.shape == (8, 1, 3, 3, 3) and blk.conv2.weight.grad.shape == (16, 8, 3, 3, 3)
+        net.eval()
+        dry.trace.clear()
+        with torch.no_grad():
+            assert net(x).shape == x.shape
+        assert dry.trace.count('ich_bn_finalize') == 1              # folded everywhere but the fused last unit
+    with config.override(precision='fp32'):
+        assert not blk._pad_mid(torch.empty(1, 8, 16, 16, 1, dtype=torch.float32))     # fp32 verification mode: untouched
