@@ -198,7 +198,14 @@ class Job:
                         b.copy_((torch.randn(b.shape, generator=gg) * 0.1).to(dev))
                     elif name.endswith('running_var'):
                         b.copy_((torch.rand(b.shape, generator=gg) + 0.5).to(dev))
-            self.host = [pin(torch.rand(*shape, generator=g))]
+            vol = torch.rand(*shape, generator=g)
+            if arm == 'b200':
+                # this repo's arm takes the volume as RAW int16 Hounsfield units (what a CT pipeline holds) and windows it on the device
+                # (ich_stage_ct, window 40 / 120 as utils/ct_utils.py:13); the reference arms get the host-windowed fp32 volume in [0, 1]
+                # that the reference's own segement_volume would upload (UNet2D.py:286-297)
+                self.host = [pin((vol * 120.0 - 20.0).round().to(torch.int16))]
+            else:
+                self.host = [pin(vol)]
 
     def _fwd(self, x):
         if self.fmt is not None:
@@ -212,8 +219,10 @@ class Job:
         import torch.nn.functional as F
         if self.kind == 'infer':
             if self.arm == 'b200':
-                from ich_b200 import infer
-                return infer.sliding_window_predict(self.net, inp[0], self.wl['window'], batch=8, distributed=self.shard_windows, return_pred=False)[1]
+                from ich_b200 import infer, ops
+                _, _, D, H, W = inp[0].shape
+                x = ops.staged(ops.stage_ct(inp[0], 40, 120, (0, 1)).view(1, D, H, W, 1))
+                return infer.sliding_window_predict(self.net, x, self.wl['window'], batch=8, distributed=self.shard_windows, return_pred=False)[1]
             return plain_sliding_window(self._fwd, inp[0], self.wl['window'], 8)
         self.opt.zero_grad()
         if self.kind == 'seg':

@@ -46,6 +46,10 @@ class GraphedStep:
         graph = torch.cuda.CUDAGraph()
         before = _lib.launches()
         try:
+            # (capture runs on a side stream: the AccumulateGrad nodes of the warm-up steps belong to the default stream, which autograd reports)
+            warn = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+            if warn is not None:
+                warn(False)
             with torch.cuda.graph(graph):
                 self.static_out = self.step_fn(*self.static_in)
         except Exception as e:      # noqa: BLE001 -- e.g. a host synchronisation inside the step (dropout seed, numpy-drawn region corners)
