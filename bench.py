@@ -345,8 +345,10 @@ def main():
                     help='--impl cudnn: bf16 autocast + channels_last(_3d), or fp32 modules with TF32 convs (torch defaults)')
     ap.add_argument('--precision', default=os.environ.get('ICH_B200_PRECISION', 'bf16'), choices=['bf16', 'fp32'])
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
-    ap.add_argument('--graph', type=int, default=int(os.environ.get('ICH_B200_CUDA_GRAPH', '0')),
-                    help='1 = run the training step through ich_b200.graph.GraphedStep (CUDA-graph replay)')
+    ap.add_argument('--graph', type=int, default=int(os.environ.get('ICH_B200_CUDA_GRAPH', '-1')),
+                    help='1 = run the training step through ich_b200.graph.GraphedStep (one CUDA-graph replay per step), 0 = eager launches; '
+                         'default: 1 on a single GPU, 0 under torchrun (replay with the captured NCCL all-reduce works -- measured at 2 and 8 '
+                         'GPUs -- but tearing the process group down with live graphs hung at 8 GPUs, so it stays opt-in there)')
     ap.add_argument('--shard', default='volume', choices=['volume', 'window'],
                     help='cfg5 at N > 1: one volume per GPU-step (weak scaling, no data-path collective) or the windows of ONE volume sharded '
                          'over the ranks with a uint8 mask exchange (strong scaling)')
@@ -388,9 +390,12 @@ def main():
     units_step = job.units if strong else world * job.units
 
     step_fn = job.step
+    if args.graph < 0:
+        args.graph = 1 if world == 1 else 0
     if args.graph and args.impl == 'b200' and job.opt is not None and job.kind != 'nce_local':     # LocalInfoNCE draws its regions on the host every step
         from ich_b200.graph import GraphedStep
-        step_fn = GraphedStep(job.step, job.opt, warmup=2)       # calls 1-2 eager, call 3 (still warm-up, >= 3 enforced above) captures
+        # calls 1-2 eager, call 3 (still warm-up, >= 3 enforced above) captures; a step that cannot be captured keeps running eagerly
+        step_fn = GraphedStep(job.step, job.opt, warmup=2, strict=False)
 
     def barrier():
         if world > 1:
@@ -497,6 +502,11 @@ def main():
             line['cpu_baseline'] = cpu
         emit(line)
     if world > 1:
+        if getattr(step_fn, 'graph', None) is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stderr.flush()
+            os._exit(0)          # live CUDA graphs hold the NCCL communicator: skip the teardown (it hung at 8 GPUs), the job is done
         dist.destroy_process_group()
 
 

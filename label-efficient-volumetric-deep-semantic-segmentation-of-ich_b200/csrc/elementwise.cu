@@ -1073,7 +1073,7 @@ __global__ void __launch_bounds__(256, U == 8 ? 2 : 3) bn_head_bwd_reduce_rows_k
 // Apply pass: dy = scale * (dz - d(beta)/M - yhat * d(gamma)/M) with dz rebuilt from d(logit); block 0 also publishes d(gamma),
 // d(beta) and the head's d(w), d(b).
 template <typename T, int U>
-__global__ void __launch_bounds__(256, U == 8 ? 2 : 3) bn_head_bwd_apply_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, U == 8 ? 2 : U == 4 ? 3 : 4) bn_head_bwd_apply_rows_kernel(const T* __restrict__ y, int y_ld, const float* __restrict__ scale,
                                                                      const float* __restrict__ shift, const float* __restrict__ mean,
                                                                      const float* __restrict__ invstd, const float* __restrict__ w,
                                                                      const float* __restrict__ out, const float* __restrict__ dout,
@@ -1513,7 +1513,7 @@ int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, cons
     // rows in flight per thread (A/B switch ICH_HEAD_BWD_U): 8 = one wave of 2 resident blocks per SM with 8 chunks in flight per thread,
     // 4 = up to 8 blocks per SM queued, 4 resident (more warps, fewer bytes in flight per warp -- the shape of the generic BatchNorm kernels)
     static int bwd_u = -1;
-    if (bwd_u < 0) { const char* e = getenv("ICH_HEAD_BWD_U"); bwd_u = (e && atoi(e) == 8) ? 8 : 4; }
+    if (bwd_u < 0) { const char* e = getenv("ICH_HEAD_BWD_U"); bwd_u = e ? atoi(e) : 4; if (bwd_u != 8 && bwd_u != 2) bwd_u = 4; }
     if (bwd_u == 8) {
       const int grid_r = one_wave_grid(bn_head_bwd_reduce_rows_kernel<T, 8>, sh_reduce, M, rpb);
       const int grid_a = one_wave_grid(bn_head_bwd_apply_rows_kernel<T, 8>, sh_apply, M, rpb);
@@ -1523,8 +1523,12 @@ int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, cons
     } else {
       const int grid = rows_grid(M, C, Vec<T>::N);
       bn_head_bwd_reduce_rows_kernel<T, 4><<<grid, 256, sh_reduce, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, M, C, relu, act, sums, hsums);
-      bn_head_bwd_apply_rows_kernel<T, 4><<<grid, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
-                                                                      dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+      if (bwd_u == 2)      // A/B: the shape of the generic BatchNorm apply kernel (2 rows per thread, 4 resident blocks per SM)
+        bn_head_bwd_apply_rows_kernel<T, 2><<<grid, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
+                                                                        dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
+      else
+        bn_head_bwd_apply_rows_kernel<T, 4><<<grid, 256, sh_apply, s>>>((const T*)y, y_ld, scale, shift, mean, invstd, w, out, dout, sums, hsums, (T*)dy,
+                                                                        dy_ld, M, C, relu, training, act, dgamma, dbeta, dw, db);
     }
   })
   return ich_check_launch("ich_bn_head_bwd");
