@@ -100,6 +100,15 @@ int ich_convT2_dgrad(const void* dy, int dy_ld, const float* wpack_d, void* dx, 
 int ich_convT2_wgrad(const void* x, int x_ld, const void* dy, int dy_ld, int dtype, float* dw, int N, int D, int H, int W, int Cin, int Cout,
                      int FD, void* stream);
 
+/* transposed-conv backward WITHOUT the re-pack: the up-sampled gradient `dup` (channel slab of the fine grid [N, FD*D, 2H, 2W, .], pitch
+ * dup_ld) is read in place through one strided tensor map per tap.  wpack_bf16 = [Cin][taps*Cout] bf16.  Grid args = the COARSE grid. */
+int ich_convT2_tc_dgrad_supported(int N, int D, int H, int W, int Cin, int Cout, int FD);
+int ich_convT2_tc_dgrad(const void* dup, int dup_ld, const void* wpack_bf16, void* dx, int dx_ld, int N, int D, int H, int W, int Cin, int Cout,
+                        int FD, void* stream);
+int ich_convT2_tc_wgrad_direct_supported(int N, int D, int H, int W, int Cin, int Cout, int FD);
+int ich_convT2_tc_wgrad_direct(const void* x, int x_ld, const void* dup, int dup_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int FD,
+                               void* stream);
+
 /* ---- BatchNorm (+ReLU): nn.BatchNorm3d/2d + nn.ReLU (models/networks/UNet.py:149,154,156,159,161,173-174) ----------- */
 int ich_colstats(const void* x, int ld, int dtype, long long M, int C, double* sum, double* sumsq, void* stream);
 int ich_bn_finalize(const double* sum, const double* sumsq, long long count, int C, const float* gamma, const float* beta,

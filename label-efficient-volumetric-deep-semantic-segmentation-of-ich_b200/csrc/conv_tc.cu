@@ -35,10 +35,17 @@ struct Params {
   int y32;   // output rows are 32-byte aligned: 256-bit stores
   int cw;    // channels per K chunk: 16 (32-byte swizzled rows) for the 3x3 kernels; 16 / 32 / 64 (32 / 64 / 128-byte rows) for the 1x1
              // GEMMs (transposed conv, heads), whose stages are small and whose TMA loads were bound by the number of 32-byte requests
+  int tap_cout;   // > 0: 1x1 GEMM whose K chunks come from the per-tap maps (transposed-conv data gradient), = Cout of the transposed conv
   int kds;   // kd-split (3-D layers with Cout % 128 == 0): a pipeline stage holds ONE input plane and the 9 taps of ONE depth tap, so that
              // a 128-wide cout block fits (9 x 128 x 32 B = 36 KB of weights per stage instead of 27 x 64 x 32 B = 55 KB): N = 128 MMAs
              // run at the full tensor rate (64 cycles) where N = 64 ones are operand-fetch bound (48 cycles for half the work)
 };
+
+// Transposed-conv backward without the space-to-depth re-pack: the up-sampled gradient dup[n][FD*d + i][2h + j][2w + l][co] is read in
+// place.  For a fixed tap (i, j, l) it is a strided view of the fine grid on the COARSE grid (element steps 2 / 2 / FD along w / h / plane),
+// i.e. an ordinary tensor map with doubled strides and a per-tap base pointer; the K chunks (data-gradient GEMM) / N chunks (weight
+// gradient GEMM) of the packed layout [voxel][tap * Cout + co] become "chunk c of tap t" = one box of map t.
+struct TapMaps { CUtensorMap m[8]; };
 
 constexpr int STAGES = 2;        // weight-gradient kernel
 constexpr int MAX_STAGES = 8;    // forward kernel: runtime depth (2 for the big 3x3 slabs, up to 8 for the small 1x1 GEMM stages)
@@ -54,7 +61,8 @@ constexpr int W_ISSUERS = 3;
 
 template <int KS, bool STATS, bool WIDE = false>
 __global__ void __launch_bounds__(f_threads<STATS, WIDE>(), 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const Params p,
+               const __grid_constant__ TapMaps tmaps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage0 A|B][stage1 A|B] ... then barriers
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -110,7 +118,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
               if (ICH_DBG(p) & 2) { mbar_arrive(&full_bar[stage]); }
               else {
                 mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_bytes);
-                tma_load_4d(sa, &map_x, &full_bar[stage], kc * p.cw, w0 - KS / 2, h0 - KS / 2, n * p.D + dd);
+                if (KS == 1 && p.tap_cout) {       // K chunk kc = channels [cc, cc + cw) of tap t, read in place from the fine grid
+                  const int col = kc * p.cw, t = col / p.tap_cout, cc = col - t * p.tap_cout;
+                  tma_load_4d(sa, &tmaps.m[t], &full_bar[stage], cc, w0, h0, n * p.D + dd);
+                } else {
+                  tma_load_4d(sa, &map_x, &full_bar[stage], kc * p.cw, w0 - KS / 2, h0 - KS / 2, n * p.D + dd);
+                }
                 tma_load_3d(sb, &map_w, &full_bar[stage], kc * p.cw, nb * p.NB, p.kds ? sub * 9 : 0);
               }
             }
@@ -323,11 +336,13 @@ struct Plan {
 };
 
 
-Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, int nb_must_divide = 0) {
+Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, int nb_must_divide = 0, int cw_must_divide = 0) {
   Plan pl;
   static int cw_env = -1;
   if (cw_env < 0) { const char* e = getenv("ICH_TC_WIDE_K"); cw_env = e ? atoi(e) : 1; }
-  const int cw = (KH == 1 && cw_env) ? (Cin % 64 == 0 ? 64 : Cin % 32 == 0 ? 32 : 16) : 16;   // channels per K chunk
+  // channels per K chunk (cw_must_divide: a chunk must not straddle two taps of the per-tap maps)
+  const int cdiv = cw_must_divide ? cw_must_divide : Cin;
+  const int cw = (KH == 1 && cw_env) ? (cdiv % 64 == 0 ? 64 : cdiv % 32 == 0 ? 32 : 16) : 16;
   const uint32_t rowb = (uint32_t)cw * 2u;                                                   // bytes per position in a stage
   if (KH != KW || (KH != 3 && KH != 1) || (KD != 1 && KD != 3) || (KH == 1 && KD != 1)) return pl;
   const int KS = KH, hw = KS / 2;
@@ -391,7 +406,7 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   if (best_cost < 0) return pl;
   Params& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
-  p.up_fd = 0; p.up_cout = 0;
+  p.up_fd = 0; p.up_cout = 0; p.tap_cout = 0;
   p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hw; p.T = bestT; p.row_mode = row_mode; p.NB = NB;
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_nb = Cout / NB; p.KC = Cin / cw; p.taps = taps; p.cw = cw;
   p.nacc = bestAcc; p.stages = bestStages;
@@ -442,8 +457,33 @@ int ich_conv_tc_plan_info(int N, int D, int H, int W, int Cin, int Cout, int KD,
   return 0;
 }
 
+// Per-tap maps of the up-sampled gradient `dup` (channel slab of the fine grid, pitch ld): map t = tap (i, j, l), dims (Cout, W, H, N*D) on
+// the COARSE grid, box (cbox, wbox, rbox, 1).
+static int make_tap_maps(TapMaps& tm, const void* dup, int ld, int N, int D, int H, int W, int Cout, int FD, int cbox, int wbox, int rbox,
+                         const char* what) {
+  EncodeTiledFn enc = get_encode();
+  ICH_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled not available", what);
+  ICH_REQUIRE((FD == 1 || FD == 2) && ld % 8 == 0 && ((uintptr_t)dup & 15) == 0 && Cout % cbox == 0, "%s: bad transposed-conv gradient layout", what);
+  const long long Wf = 2LL * W, Hf = 2LL * H;
+  const CUtensorMapSwizzle sw = cbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : cbox == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  for (int t = 0; t < 4 * FD; ++t) {
+    const int i = FD == 2 ? (t >> 2) : 0, j = (t >> 1) & 1, l = t & 1;
+    const char* base = (const char*)dup + (((long long)i * Hf + j) * Wf + l) * ld * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
+    cuuint64_t strides[3] = {(cuuint64_t)2 * ld * 2, (cuuint64_t)2 * Wf * ld * 2, (cuuint64_t)FD * Hf * Wf * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)cbox, (cuuint32_t)wbox, (cuuint32_t)rbox, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm.m[t], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(tap %d) failed with %d", what, t, (int)r);
+  }
+  for (int t = 4 * FD; t < 8; ++t) tm.m[t] = tm.m[0];
+  return 0;
+}
+
 static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int relu,
-                          cudaStream_t stream, const char* what, double* stat_sum = nullptr, double* stat_sumsq = nullptr) {
+                          cudaStream_t stream, const char* what, double* stat_sum = nullptr, double* stat_sumsq = nullptr,
+                          const TapMaps* tap_maps = nullptr) {
   Params& p = pl.p;
   const int N = p.N, D = p.D, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout, KD = p.KD;
   ICH_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wpack_bf16 & 15) == 0,
@@ -462,7 +502,8 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   }
 
   CUtensorMap map_x, map_w;
-  {
+  if (p.tap_cout) map_x = tap_maps->m[0];      // the A operand comes from the per-tap maps
+  else {
     // x as (C, W, H, N*D): the box lands as [plane][row][pos][16 ch] = 32-byte rows, 32B-swizzled (full 32 B L2 sectors)
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * D};
     cuuint64_t strides[3] = {(cuuint64_t)x_ld * 2, (cuuint64_t)W * x_ld * 2, (cuuint64_t)H * W * x_ld * 2};
@@ -500,10 +541,12 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
   grid = grid / p.n_nb * p.n_nb;             // every CTA owns one cout block; n_items is a multiple of n_nb
   if (grid < p.n_nb) grid = p.n_nb;
-  if (p.KS == 3 && stat_sum && p.NB == 128) conv_tc_kernel<3, true, true><<<(unsigned)grid, f_threads<true, true>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else if (p.KS == 3 && stat_sum) conv_tc_kernel<3, true><<<(unsigned)grid, f_threads<true>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else if (p.KS == 3) conv_tc_kernel<3, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else conv_tc_kernel<1, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p);
+  static TapMaps no_taps;      // unused unless p.tap_cout (zero-initialised; passed by value as a kernel parameter)
+  const TapMaps& tm = tap_maps ? *tap_maps : no_taps;
+  if (p.KS == 3 && stat_sum && p.NB == 128) conv_tc_kernel<3, true, true><<<(unsigned)grid, f_threads<true, true>(), pl.smem_bytes, stream>>>(map_x, map_w, p, tm);
+  else if (p.KS == 3 && stat_sum) conv_tc_kernel<3, true><<<(unsigned)grid, f_threads<true>(), pl.smem_bytes, stream>>>(map_x, map_w, p, tm);
+  else if (p.KS == 3) conv_tc_kernel<3, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p, tm);
+  else conv_tc_kernel<1, false><<<(unsigned)grid, f_threads<false>(), pl.smem_bytes, stream>>>(map_x, map_w, p, tm);
   return ich_check_launch(what);
 }
 
@@ -545,6 +588,25 @@ int ich_convT2_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const flo
   return launch_conv_tc(pl, x, x_ld, wpack_bf16, bias, y, y_ld, 0, (cudaStream_t)stream, "ich_convT2_tc_fwd");
 }
 
+// Transposed conv k2 s2 data gradient straight from the up-sampled gradient (no space-to-depth re-pack): dx[v][ci] = sum_{tap, co}
+// dup[fine(v, tap)][co] * W[ci][co][tap] = a 1x1 GEMM over K = taps * Cout whose K chunks are boxes of the per-tap maps.
+// wpack_bf16 = [Cin][taps * Cout] bf16 (ops pack 'convT_dgrad_tc').  Grid args = the COARSE grid; dup = channel slab of the fine grid.
+int ich_convT2_tc_dgrad(const void* dup, int dup_ld, const void* wpack_bf16, void* dx, int dx_ld, int N, int D, int H, int W, int Cin, int Cout,
+                        int FD, void* stream) {
+  ICH_REQUIRE((FD == 1 || FD == 2) && Cout % 16 == 0, "ich_convT2_tc_dgrad: unsupported FD %d / Cout %d", FD, Cout);
+  Plan pl = make_plan(N, D, H, W, 4 * FD * Cout, Cin, 1, 1, 1, 0, Cout);
+  ICH_REQUIRE(pl.ok, "ich_convT2_tc_dgrad: unsupported shape N%d D%d H%d W%d Cin%d Cout%d", N, D, H, W, Cin, Cout);
+  pl.p.tap_cout = Cout;
+  TapMaps tm;
+  if (int rc = make_tap_maps(tm, dup, dup_ld, N, D, H, W, Cout, FD, pl.p.cw, pl.p.PW, pl.p.RB, "ich_convT2_tc_dgrad")) return rc;
+  return launch_conv_tc(pl, dup, dup_ld, wpack_bf16, nullptr, dx, dx_ld, 0, (cudaStream_t)stream, "ich_convT2_tc_dgrad", nullptr, nullptr, &tm);
+}
+
+int ich_convT2_tc_dgrad_supported(int N, int D, int H, int W, int Cin, int Cout, int FD) {
+  if (!get_encode() || (FD != 1 && FD != 2) || Cout % 16) return 0;
+  return make_plan(N, D, H, W, 4 * FD * Cout, Cin, 1, 1, 1, 0, Cout).ok ? 1 : 0;
+}
+
 }  // extern "C"
 
 // =====================================================================================================================
@@ -577,11 +639,13 @@ struct WParams {
   int splits;
   float* dw;
   int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA loads
+  int tap_cout;   // > 0: transposed-conv weight gradient with dy read in place from the fine grid through the per-tap maps (= its Cout)
 };
 
 template <int KS>
 __global__ void __launch_bounds__(W_THREADS, 1)
-conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p) {
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WParams p,
+                     const __grid_constant__ TapMaps tmaps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
@@ -635,7 +699,16 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             tma_load_5d(sa + (size_t)pl * p.plane_bytes, &map_x, &full_bar[stage], 0, w0 - KS / 2, h0 - KS / 2 + khf, cb * (p.CU / (p.a64 ? 32 : 16)), coord);
           }
           if (p.kwf) tma_load_4d(sb, &map_dy, &full_bar[stage], nb * p.NB, w0 - 1, h0, n * p.D + d);
-          else tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / (8 * p.bu)), n * p.D + d);
+          else if (KS == 1 && p.tap_cout) {
+            // the N block = NB / cbk channel chunks; chunk q = channels [cc, cc + cbk) of tap t, one box of map t each, laid out exactly
+            // as the single 5-D box of the packed layout would land them ([chunk][row][pos][cbk])
+            const int cbk = 8 * p.bu;
+            const uint32_t chunk_bytes = (uint32_t)p.R * p.WB * cbk * 2u;
+            for (int q = 0; q < p.NB / cbk; ++q) {
+              const int col = nb * p.NB + q * cbk, t = col / p.tap_cout, cc = col - t * p.tap_cout;
+              tma_load_4d(sb + (size_t)q * chunk_bytes, &tmaps.m[t], &full_bar[stage], cc, w0, h0, n * p.D + d);
+            }
+          } else tma_load_5d(sb, &map_dy, &full_bar[stage], 0, w0, h0, nb * (p.NB / (8 * p.bu)), n * p.D + d);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -803,7 +876,7 @@ WPlan make_wplan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, 
   if (!bestR) return pl;
   WParams& p = pl.p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KD = KD; p.KS = KS;
-  p.out_mode = 0; p.up_cout = 0; p.taps_out = 0; p.khs = khs ? 1 : 0;
+  p.out_mode = 0; p.up_cout = 0; p.taps_out = 0; p.khs = khs ? 1 : 0; p.tap_cout = 0;
   p.WB = WB; p.PW = PW; p.R = bestR; p.RB = bestR + 2 * hwr; p.CU = CU; p.NB = NB; p.chunks_u = chunks_u; p.chunks_v = chunks_v;
   p.n_wb = (W + WB - 1) / WB; p.n_rb = (H + bestR - 1) / bestR; p.n_cb = Cin / CU; p.n_nb = Cout / NB;
   p.plane_bytes = (uint32_t)chunks_u * p.RB * PW * 16u;
@@ -842,7 +915,7 @@ int ich_conv_tc_wgrad_supported(int N, int D, int H, int W, int Cin, int Cout, i
 }
 
 static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* dy, int dy_ld, float* dw, size_t dw_elems, cudaStream_t s,
-                                const char* what) {
+                                const char* what, const TapMaps* tap_maps = nullptr) {
   WParams& p = pl.p;
   const int N = p.N, D = p.D, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout;
   ICH_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
@@ -875,6 +948,8 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(dy, kw-fold) failed with %d", what, (int)r);
+  } else if (p.tap_cout) {
+    map_dy = tap_maps->m[0];                          // dy comes from the per-tap maps
   } else {
     const cuuint32_t cbk = 8u * (cuuint32_t)p.bu;     // channels per block = one swizzled row (16 / 32 / 64)
     cuuint64_t dims[5] = {cbk, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / cbk), (cuuint64_t)N * D};
@@ -896,8 +971,10 @@ static int launch_conv_tc_wgrad(WPlan& pl, const void* x, int x_ld, const void* 
     attr_set = true;
   }
   dim3 grid((unsigned)p.splits, (unsigned)(p.n_cb * p.n_nb * (p.khs ? 3 : 1)));
-  if (p.KS == 3) conv_tc_wgrad_kernel<3><<<grid, W_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
-  else conv_tc_wgrad_kernel<1><<<grid, W_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p);
+  static TapMaps no_taps;
+  const TapMaps& tm = tap_maps ? *tap_maps : no_taps;
+  if (p.KS == 3) conv_tc_wgrad_kernel<3><<<grid, W_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p, tm);
+  else conv_tc_wgrad_kernel<1><<<grid, W_THREADS, pl.smem_bytes, s>>>(map_x, map_dy, p, tm);
   return ich_check_launch(what);
 }
 
@@ -966,6 +1043,38 @@ int ich_convT2_tc_wgrad(const void* x, int x_ld, const void* g, int g_ld, float*
   pl.p.up_cout = Cout;
   pl.p.taps_out = 4 * FD;
   return launch_conv_tc_wgrad(pl, x, x_ld, g, g_ld, dw, (size_t)Cin * Cout * 4 * FD, (cudaStream_t)stream, "ich_convT2_tc_wgrad");
+}
+
+// The same weight gradient with the up-sampled gradient `dup` (channel slab of the FINE grid, pitch dup_ld) read in place through the per-tap
+// maps -- no re-packed copy.  Needs the dy channel chunk (16 / 32 / 64) to divide Cout.
+static bool convT2_wgrad_direct_plan(WPlan& pl, int N, int D, int H, int W, int Cin, int Cout, int FD) {
+  pl = make_wplan(N, D, H, W, Cin, 4 * FD * Cout, 1, 1, 1);
+  if (!pl.ok) return false;
+  int cbk = 8 * pl.p.bu;
+  while (cbk > 16 && Cout % cbk) cbk >>= 1;          // a channel chunk must not straddle two taps
+  if (Cout % cbk || pl.p.NB % cbk) return false;
+  pl.p.bu = cbk / 8;
+  return true;
+}
+
+int ich_convT2_tc_wgrad_direct_supported(int N, int D, int H, int W, int Cin, int Cout, int FD) {
+  if (!get_encode() || (FD != 1 && FD != 2) || Cout % 16) return 0;
+  WPlan pl;
+  return convT2_wgrad_direct_plan(pl, N, D, H, W, Cin, Cout, FD) ? 1 : 0;
+}
+
+int ich_convT2_tc_wgrad_direct(const void* x, int x_ld, const void* dup, int dup_ld, float* dw, int N, int D, int H, int W, int Cin, int Cout, int FD,
+                               void* stream) {
+  WPlan pl;
+  ICH_REQUIRE((FD == 1 || FD == 2) && Cout % 16 == 0 && convT2_wgrad_direct_plan(pl, N, D, H, W, Cin, Cout, FD),
+              "ich_convT2_tc_wgrad_direct: unsupported shape N%d D%d H%d W%d Cin%d Cout%d FD%d", N, D, H, W, Cin, Cout, FD);
+  pl.p.out_mode = 1;
+  pl.p.up_cout = Cout;
+  pl.p.taps_out = 4 * FD;
+  pl.p.tap_cout = Cout;
+  TapMaps tm;
+  if (int rc = make_tap_maps(tm, dup, dup_ld, N, D, H, W, Cout, FD, 8 * pl.p.bu, pl.p.WB, pl.p.R, "ich_convT2_tc_wgrad_direct")) return rc;
+  return launch_conv_tc_wgrad(pl, x, x_ld, dup, dup_ld, dw, (size_t)Cin * Cout * 4 * FD, (cudaStream_t)stream, "ich_convT2_tc_wgrad_direct", &tm);
 }
 
 }  // extern "C"

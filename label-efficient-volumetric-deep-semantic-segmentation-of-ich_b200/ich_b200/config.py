@@ -30,6 +30,9 @@ _state = {
     # re-derive the kernel-layout weight packs from a global optimizer post-step hook (hidden behind the GPU's backlog) instead of at
     # the start of the next forward pass (0 = only there)
     'refresh_after_step': os.environ.get('ICH_B200_REFRESH_AFTER_STEP', '1') == '1',
+    # transposed-conv backward reads the up-sampled gradient in place (one strided tensor map per tap) instead of re-packing it to the
+    # coarse grid first (ich_space_to_depth2: a 4 B/element pass); 0 = the re-pack path
+    'convt_direct': os.environ.get('ICH_B200_CONVT_DIRECT', '1') == '1',
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

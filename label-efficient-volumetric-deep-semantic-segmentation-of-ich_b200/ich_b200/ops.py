@@ -772,7 +772,21 @@ class UpConvCat(Function):
             dres = dout[..., :cres]                      # zero-copy: consumers take the channel pitch explicitly
         dup = dout[..., cres:]
         dx = dw = db = None
-        if ctx.use_tc and (need[0] or need[2]):
+        from ._lib import lib
+        if ctx.use_tc and (need[0] or need[2]) and config.get('convt_direct') and \
+                lib().ich_convT2_tc_dgrad_supported(n, d, h, w, cin, cout, fd) and lib().ich_convT2_tc_wgrad_direct_supported(n, d, h, w, cin, cout, fd):
+            # both gradients are 1x1 GEMMs over [voxel][tap*Cout + co]; their operand chunks are read IN PLACE from the fine-grid gradient
+            # through one strided tensor map per tap (no re-packed copy); the bias gradient is the column-sum pass at the end
+            if need[0]:
+                dx = torch.empty_like(x)
+                call('ich_convT2_tc_dgrad', dup.data_ptr(), ctot, _p(_pack(weight, 'convT_dgrad_tc')), dx.data_ptr(), cin, n, d, h, w, cin, cout, fd,
+                     _stream())
+            if need[2]:
+                dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+                xp, xld = _rows(x)
+                call('ich_convT2_tc_wgrad_direct', xp, xld, dup.data_ptr(), ctot, dw.data_ptr(), n, d, h, w, cin, cout, fd, _stream())
+            need = (False, need[1], False, need[3], need[4])
+        elif ctx.use_tc and (need[0] or need[2]):
             # re-pack the up-sampled gradient to the coarse grid once ([voxel][tap*Cout + co]); both gradients are then 1x1 GEMMs
             taps = 4 * fd
             g = torch.empty((n, d, h, w, taps * cout), dtype=dout.dtype, device=dout.device)

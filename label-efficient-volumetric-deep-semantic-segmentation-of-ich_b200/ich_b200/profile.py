@@ -35,7 +35,7 @@ TABLE = {
     'ich_conv_tc_fwd': _conv, 'ich_conv_tc_fwd_stats': _conv, 'ich_conv_fwd': _conv, 'ich_conv_cin1_tc_fwd': _conv,
     'ich_conv_tc_wgrad': lambda a, t: _conv(a, 'wgrad'), 'ich_conv_wgrad': lambda a, t: _conv(a, 'wgrad'),
     'ich_conv_cin1_tc_wgrad': lambda a, t: _conv(a, 'wgrad'),
-    'ich_convT2_tc_fwd': _convT, 'ich_convT2_fwd': _convT, 'ich_convT2_tc_wgrad': _convT, 'ich_convT2_wgrad': _convT, 'ich_convT2_dgrad': _convT,
+    'ich_convT2_tc_fwd': _convT, 'ich_convT2_fwd': _convT, 'ich_convT2_tc_dgrad': _convT, 'ich_convT2_tc_wgrad_direct': _convT, 'ich_convT2_tc_wgrad': _convT, 'ich_convT2_wgrad': _convT, 'ich_convT2_dgrad': _convT,
     'ich_affine_act': _bw('bn_apply', lambda a: 2 * a['M'] * a['C'] * _es(a)),
     'ich_affine_act_drop': _bw('bn_apply', lambda a: 2 * a['M'] * a['C'] * _es(a)),
     'ich_bn_act_bwd': _bw('bn_bwd', lambda a: 5 * a['M'] * a['C'] * _es(a)),
