@@ -1513,7 +1513,7 @@ int ich_bn_head_bwd(const void* y, int y_ld, int dtype, const float* scale, cons
     // rows in flight per thread (A/B switch ICH_HEAD_BWD_U): 8 = one wave of 2 resident blocks per SM with 8 chunks in flight per thread,
     // 4 = up to 8 blocks per SM queued, 4 resident (more warps, fewer bytes in flight per warp -- the shape of the generic BatchNorm kernels)
     static int bwd_u = -1;
-    if (bwd_u < 0) { const char* e = getenv("ICH_HEAD_BWD_U"); bwd_u = e ? atoi(e) : 4; if (bwd_u != 8 && bwd_u != 2) bwd_u = 4; }
+    if (bwd_u < 0) { const char* e = getenv("ICH_HEAD_BWD_U"); bwd_u = e ? atoi(e) : 2; if (bwd_u != 8 && bwd_u != 4) bwd_u = 2; }   // measured: head family 0.59 (4) -> 0.50 ms (2) per cfg-3 step
     if (bwd_u == 8) {
       const int grid_r = one_wave_grid(bn_head_bwd_reduce_rows_kernel<T, 8>, sh_reduce, M, rpb);
       const int grid_a = one_wave_grid(bn_head_bwd_apply_rows_kernel<T, 8>, sh_apply, M, rpb);

@@ -33,6 +33,9 @@ _state = {
     # transposed-conv backward reads the up-sampled gradient in place (one strided tensor map per tap) instead of re-packing it to the
     # coarse grid first (ich_space_to_depth2: a 4 B/element pass); 0 = the re-pack path
     'convt_direct': os.environ.get('ICH_B200_CONVT_DIRECT', '1') == '1',
+    # the transposed conv's bias gradient (column sums of the up-sampled gradient) is taken in the statistics epilogue of the data-gradient
+    # conv that produces that tensor; 0 = a separate column-sum pass over it
+    'dgrad_colsum': os.environ.get('ICH_B200_DGRAD_COLSUM', '1') == '1',
     # use the tcgen05 kernels when the shape is eligible (bf16 mode only)
     'tensor_cores': os.environ.get('ICH_B200_TENSOR_CORES', '1') == '1',
 }

@@ -289,22 +289,29 @@ def _conv_forward(x, weight, bias, relu):
     return y
 
 
-def conv_dgrad(dy, weight):
+def conv_dgrad(dy, weight, want_colsum=False):
+    """want_colsum: also return the fp64 per-channel sums of the stored gradient when the tcgen05 kernel can take them in its epilogue
+    (the transposed conv that produced the tensor needs them as its bias gradient); attached to the result as `_ich_colsum`."""
     n, d, h, w, cout = dy.shape
     cin = weight.shape[1]
     k = _ksize(weight)
     with _Timed('dgrad', 2.0 * n * d * h * w * cin * cout * k[0] * k[1] * k[2]):
-        return _conv_dgrad(dy, weight)
+        return _conv_dgrad(dy, weight, want_colsum)
 
 
-def _conv_dgrad(dy, weight):
+def _conv_dgrad(dy, weight, want_colsum=False):
     n, d, h, w, cout = dy.shape
     cin = weight.shape[1]
     k = _ksize(weight)
     dx = torch.empty((n, d, h, w, cin), dtype=dy.dtype, device=dy.device)
     yp, yld = _rows(dy)
     var = _tc_variant(dy, cout, cin, k)
-    if var:
+    if var and want_colsum and k[1] == 3:
+        sums = torch.empty((2, cin), dtype=torch.float64, device=dy.device)
+        call('ich_conv_tc_fwd_stats', yp, yld, _p(_pack(weight, 'conv_dgrad_tc_s' if var == 2 else 'conv_dgrad_tc')), dx.data_ptr(), cin,
+             sums[0].data_ptr(), sums[1].data_ptr(), n, d, h, w, cout, cin, *k, _stream())
+        dx._ich_colsum = sums[0]
+    elif var:
         call('ich_conv_tc_fwd', yp, yld, _p(_pack(weight, 'conv_dgrad_tc_s' if var == 2 else 'conv_dgrad_tc')), None, dx.data_ptr(), cin,
              n, d, h, w, cout, cin, *k, 0, _stream())
     else:
@@ -508,6 +515,7 @@ class ConvBnRelu(Function):
         ctx.save_for_backward(x, weight, y, stats)
         ctx.training, ctx.relu, ctx.drop = training, relu, (drop_p, seed)
         ctx.sync = synced
+        ctx.colsum = bool(getattr(x, '_ich_upcat', False))      # the input is UpConvCat's buffer: its backward wants the column sums of dx
         if concat_c:
             ctx.mark_non_differentiable(buf)
             return z, buf
@@ -547,7 +555,7 @@ class ConvBnRelu(Function):
                  stats[3].data_ptr(), sums.data_ptr(), dy.data_ptr(), cout, dgamma.data_ptr(), dbeta.data_ptr(), _dt(y), m, cout, int(ctx.relu),
                  int(ctx.training), _stream())
         need = ctx.needs_input_grad
-        dx = conv_dgrad(dy, weight) if need[0] else None
+        dx = conv_dgrad(dy, weight, want_colsum=ctx.colsum) if need[0] else None
         dw = conv_wgrad(x, dy, weight) if need[1] else None
         db = None
         if need[2]:
@@ -755,6 +763,8 @@ class UpConvCat(Function):
                  _stream())
         ctx.save_for_backward(x, weight)
         ctx.fd, ctx.cres, ctx.use_tc = fd, cres, use_tc
+        # the consuming conv's data-gradient epilogue then sums the bias gradient on the way (ICH_B200_DGRAD_COLSUM=0: a separate pass)
+        out._ich_upcat = bool(use_tc and bias is not None and config.get('dgrad_colsum'))
         return out
 
     @staticmethod
@@ -772,6 +782,10 @@ class UpConvCat(Function):
             dres = dout[..., :cres]                      # zero-copy: consumers take the channel pitch explicitly
         dup = dout[..., cres:]
         dx = dw = db = None
+        colsum = getattr(dout, '_ich_colsum', None)           # per-channel sums of dout from the epilogue of the kernel that produced it
+        if need[3] and colsum is not None and colsum.shape[0] == ctot:
+            db = colsum[cres:].float()
+            need = (need[0], need[1], need[2], False, need[4])
         from ._lib import lib
         if ctx.use_tc and (need[0] or need[2]) and config.get('convt_direct') and \
                 lib().ich_convT2_tc_dgrad_supported(n, d, h, w, cin, cout, fd) and lib().ich_convT2_tc_wgrad_direct_supported(n, d, h, w, cin, cout, fd):
