@@ -392,7 +392,8 @@ def main():
     step_fn = job.step
     if args.graph < 0:
         args.graph = 1 if world == 1 else 0
-    if args.graph and args.impl == 'b200' and job.opt is not None and job.kind != 'nce_local':     # LocalInfoNCE draws its regions on the host every step
+    capturable = (job.opt is not None and job.kind != 'nce_local') or (job.kind == 'infer' and not getattr(job, 'shard_windows', False))
+    if args.graph and args.impl == 'b200' and capturable:     # (LocalInfoNCE draws its regions on the host every step: never captured)
         from ich_b200.graph import GraphedStep
         # calls 1-2 eager, call 3 (still warm-up, >= 3 enforced above) captures; a step that cannot be captured keeps running eagerly
         step_fn = GraphedStep(job.step, job.opt, warmup=2, strict=False)

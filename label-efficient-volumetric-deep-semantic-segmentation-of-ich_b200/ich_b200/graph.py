@@ -20,7 +20,10 @@ from . import _lib
 
 class GraphedStep:
     def __init__(self, step_fn, optimizer=None, warmup=3, strict=True):
-        """strict=False: a step that cannot be captured keeps running eagerly (`failed` holds the reason) instead of raising."""
+        """step_fn(*device_tensors) -> tensor: a training step (pass its optimizer) or any fixed-shape inference call, e.g.
+        `lambda vol: infer.sliding_window_predict(net, vol, window, return_pred=False)[1]` (its window corners are cached on the device
+        after the first call, so the rest is pure kernel launches).
+        strict=False: a step that cannot be captured keeps running eagerly (`failed` holds the reason) instead of raising."""
         self.step_fn = step_fn
         self.strict = strict
         self.failed = None

@@ -19,6 +19,9 @@ from . import config, ops
 from .dp import shard_indices
 
 
+_STARTS = {}      # (window corners of this rank, device) -> int32 device tensor
+
+
 def window_starts(L, w, s):
     return sorted(set(list(range(0, max(L - w, 0) + 1, s)) + [max(L - w, 0)]))
 
@@ -77,7 +80,14 @@ def sliding_window_predict(net, vol, window, stride=None, batch=4, threshold=0.5
     v = _one_channel_engine_volume(vol)
     with torch.no_grad():
         if mine:
-            starts_all = torch.tensor(mine, dtype=torch.int32, device=dev)
+            # window corners on the device, uploaded once per (geometry, shard, device): the call itself then makes no host -> device copy
+            # and no synchronisation, so a fixed-shape inference loop can be replayed as one CUDA graph (ich_b200.graph.GraphedStep)
+            key = (tuple(mine), str(dev))
+            starts_all = _STARTS.get(key)
+            if starts_all is None:
+                if len(_STARTS) > 64:
+                    _STARTS.clear()
+                starts_all = _STARTS[key] = torch.tensor(mine, dtype=torch.int32, device=dev)
         for i in range(0, len(mine), batch):
             starts = starts_all[i:i + batch].contiguous()
             x = ops.staged(ops.window_gather(v, starts, window))
