@@ -332,7 +332,16 @@ class UNet(_UNetBase):
             out = self._decode(x, res, head=(self.final_conv, act))                          # UNet.py:119 + :122, fused
         else:
             x = self._decode(x, res)
-            out = ops.Head.apply(x, self.final_conv.weight, self.final_conv.bias, act)       # UNet.py:122
+            fc = self.final_conv
+            if fc.in_channels > 64 and fc.out_channels <= 8:
+                # the head kernel keeps its weights in shared memory (<= 64 input channels): wider nets (top_filter = 128) run the 1x1 conv
+                # on the conv kernels and use the head kernel for the activation + fp32 NC(D)HW layout only (identity weights)
+                logits = ops.ConvBias.apply(x, fc.weight, fc.bias, False)
+                c = fc.out_channels
+                eye = torch.eye(c, dtype=torch.float32, device=logits.device).view(c, c, *([1] * (fc.weight.dim() - 2)))
+                out = ops.Head.apply(logits, eye, None, act)
+            else:
+                out = ops.Head.apply(x, fc.weight, fc.bias, act)                                 # UNet.py:122
         _flush_nbt()
         if was_4d:
             out = out.squeeze(2)

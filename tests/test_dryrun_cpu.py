@@ -356,3 +356,14 @@ def test_padded_mid_channels_plumbing(dry):
         assert dry.trace.count('ich_bn_finalize') == 1              # folded everywhere but the fused last unit
     with config.override(precision='fp32'):
         assert not blk._pad_mid(torch.empty(1, 8, 16, 16, 1, dtype=torch.float32))     # fp32 verification mode: untouched
+
+
+def test_wide_head_plumbing(dry):
+    """top_filter = 128 with a multi-class head: the 1x1 conv runs on the conv kernels, the head kernel does activation + layout."""
+    from src.models.networks.UNet import UNet
+    net = UNet(depth=2, use_3D=False, top_filter=128, out_channels=3, p_dropout=0.0).train()
+    out = net(torch.rand(1, 1, 8, 16))
+    assert out.shape == (1, 3, 8, 16)
+    out.sum().backward()
+    _grads_ok(net)
+    assert dry.trace.count('ich_head_fwd') == 1 and 'ich_head_dlogit' in dry.trace

@@ -670,3 +670,20 @@ def test_reference_trainer_on_the_drop_in(tmp_path):
     # bf16 engine: trains to the same quality
     assert all(np.isfinite(e[1]) for e in b16['evolution']) and b16['evolution'][-1][1] < b16['evolution'][0][1]
     assert abs(b16['dice']['all'] - ref['dice']['all']) < 5e-2
+
+
+def test_wide_multiclass_head_fp32():
+    """`UNet(top_filter=128)` with a softmax head (more input channels than the head kernel's shared-memory table)."""
+    from src.models.networks.UNet import UNet
+    kw = dict(depth=2, use_3D=False, in_channels=1, out_channels=3, top_filter=128, midchannels_factor=2, p_dropout=0.0)
+    _, sd = seeded(UNet, kw)
+    x = torch.rand(2, 1, 16, 32, generator=torch.Generator().manual_seed(7))
+    ref = UO.unet_forward(x, sd, use_3D=False, training=True)
+    with config.override(precision='fp32'):
+        net = UNet(**kw)
+        net.load_state_dict(sd)
+        net = net.to(DEV).train()
+        out = net(x.to(DEV))
+        out[:, 0].sum().backward()
+    assert rel(out, ref) < 1e-4 and torch.equal(out.argmax(1).cpu(), ref.argmax(1))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
