@@ -424,8 +424,8 @@ def main():
     l0 = _lib.launches() if _lib else 0
     t_dev = timed(lambda: step_fn(*dev_in), args.steps)
     launches = (_lib.launches() - l0) if _lib else 0
-    if args.graph and _lib:
-        launches = getattr(step_fn, 'kernels_per_replay', 0) * args.steps
+    if _lib and getattr(step_fn, 'graph', None) is not None:       # replayed: the launches recorded at capture time run once per replay
+        launches = step_fn.kernels_per_replay * args.steps
 
     # end to end through the public API: every step's inputs come from pinned HOST memory (copied inside the timed region,
     # one batch of look-ahead on a side stream = ich_b200.staging.DevicePrefetcher) and the result is read back to the host
