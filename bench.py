@@ -346,9 +346,8 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('ICH_B200_PRECISION', 'bf16'), choices=['bf16', 'fp32'])
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
     ap.add_argument('--graph', type=int, default=int(os.environ.get('ICH_B200_CUDA_GRAPH', '-1')),
-                    help='1 = run the training step through ich_b200.graph.GraphedStep (one CUDA-graph replay per step), 0 = eager launches; '
-                         'default: 1 on a single GPU, 0 under torchrun (replay with the captured NCCL all-reduce works -- measured at 2 and 8 '
-                         'GPUs -- but tearing the process group down with live graphs hung at 8 GPUs, so it stays opt-in there)')
+                    help='1 = run the step through ich_b200.graph.GraphedStep (one CUDA-graph replay per step; under torchrun the bucketed NCCL '
+                         'all-reduce is captured with it -- measured at 2 and 8 GPUs), 0 = eager launches; default 1')
     ap.add_argument('--shard', default='volume', choices=['volume', 'window'],
                     help='cfg5 at N > 1: one volume per GPU-step (weak scaling, no data-path collective) or the windows of ONE volume sharded '
                          'over the ranks with a uint8 mask exchange (strong scaling)')
@@ -391,7 +390,7 @@ def main():
 
     step_fn = job.step
     if args.graph < 0:
-        args.graph = 1 if world == 1 else 0
+        args.graph = 1
     capturable = (job.opt is not None and job.kind != 'nce_local') or (job.kind == 'infer' and not getattr(job, 'shard_windows', False))
     if args.graph and args.impl == 'b200' and capturable:     # (LocalInfoNCE draws its regions on the host every step: never captured)
         from ich_b200.graph import GraphedStep
@@ -504,10 +503,13 @@ def main():
         emit(line)
     if world > 1:
         if getattr(step_fn, 'graph', None) is not None:
+            # live CUDA graphs hold the NCCL communicator and destroy_process_group() hung with them at 8 GPUs: the job is done, so leave
+            # without the teardown -- and never later than 20 s from now, whatever the barrier does
+            threading.Timer(20.0, lambda: os._exit(0)).start()
             dist.barrier()
             torch.cuda.synchronize()
             sys.stderr.flush()
-            os._exit(0)          # live CUDA graphs hold the NCCL communicator: skip the teardown (it hung at 8 GPUs), the job is done
+            os._exit(0)
         dist.destroy_process_group()
 
 
