@@ -257,7 +257,8 @@ class _UNetBase(nn.Module):
                                f'(the reference has no pad/crop logic either, UNet.py:117-119)')
 
     def _encode(self, x):
-        self._check_grid(x, len(self.down_block))
+        if len(getattr(self, 'up_samp', [])):           # a decoder concatenates with the skip tensors: sizes must halve exactly
+            self._check_grid(x, len(self.down_block))   # (encoder-only nets pool with floor, as nn.MaxPool does, UNet.py:82,313)
         res = []
         n_down = len(self.down_block)
         ups = list(getattr(self, 'up_samp', []))

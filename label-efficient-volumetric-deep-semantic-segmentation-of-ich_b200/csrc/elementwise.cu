@@ -1337,7 +1337,10 @@ int ich_bn_act_bwd_sync(const void* dz, int dz_ld, const void* y, int y_ld, cons
 
 static int maxpool2_fwd_impl(const void* x, int x_ld, void* y, int y_ld, void* skip, int skip_ld, int dtype, int N, int D, int H, int W, int C,
                              int FD, cudaStream_t s, const char* what) {
-  ICH_REQUIRE((FD == 1 || FD == 2) && D % FD == 0 && H % 2 == 0 && W % 2 == 0, "%s: grid %dx%dx%d not divisible by the pool", what, D, H, W);
+  // odd sizes: nn.MaxPool floors (models/networks/UNet.py:82), the last plane / row / column is simply not pooled -- except with a skip
+  // destination, which must receive EVERY voxel (the kernel walks the pooled windows only)
+  ICH_REQUIRE(FD == 1 || FD == 2, "%s: depth factor %d", what, FD);
+  ICH_REQUIRE(!skip || (D % FD == 0 && H % 2 == 0 && W % 2 == 0), "%s: grid %dx%dx%d not divisible by the pool (skip copy fused)", what, D, H, W);
   long long outv = (long long)N * (D / FD) * (H / 2) * (W / 2);
   if (outv * C == 0) return 0;
   DISPATCH_T(dtype, what, {
@@ -1362,7 +1365,10 @@ int ich_maxpool2_fwd_skip(const void* x, int x_ld, void* y, int y_ld, void* skip
 int ich_maxpool2_bwd(const void* x, int x_ld, const void* dy, int dy_ld, void* dx, int dx_ld, int dtype, int N, int D, int H, int W,
                      int C, int FD, const void* dskip, int dskip_ld, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  ICH_REQUIRE((FD == 1 || FD == 2) && D % FD == 0 && H % 2 == 0 && W % 2 == 0, "ich_maxpool2_bwd: grid %dx%dx%d not divisible by the pool", D, H, W);
+  // odd sizes (floor pooling): voxels outside every window get no pooled gradient -- the CALLER zero-fills dx first; a skip gradient
+  // would have to reach them too, so that combination is refused
+  ICH_REQUIRE(FD == 1 || FD == 2, "ich_maxpool2_bwd: depth factor %d", FD);
+  ICH_REQUIRE(!dskip || (D % FD == 0 && H % 2 == 0 && W % 2 == 0), "ich_maxpool2_bwd: grid %dx%dx%d not divisible by the pool (skip gradient fused)", D, H, W);
   long long outv = (long long)N * (D / FD) * (H / 2) * (W / 2);
   if (outv * C == 0) return 0;
   DISPATCH_T(dtype, "ich_maxpool2_bwd", {

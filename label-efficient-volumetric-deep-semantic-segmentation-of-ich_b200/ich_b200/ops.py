@@ -676,7 +676,8 @@ class MaxPool2(Function):
         (x,) = ctx.saved_tensors
         n, d, h, w, c = x.shape
         dy = dy.contiguous()
-        dx = torch.empty((n, d, h, w, c), dtype=x.dtype, device=x.device)
+        odd = d % ctx.fd or h % 2 or w % 2          # floor pooling: the un-pooled tail receives no gradient
+        dx = (torch.zeros if odd else torch.empty)((n, d, h, w, c), dtype=x.dtype, device=x.device)
         xp, xld = _rows(x)
         call('ich_maxpool2_bwd', xp, xld, dy.data_ptr(), c, dx.data_ptr(), c, _dt(x), n, d, h, w, c, ctx.fd, None, 0, _stream())
         return dx, None
@@ -696,6 +697,7 @@ class PoolSkip(Function):
         xp, xld = _rows(x)
         ctx.save_for_backward(x)
         ctx.fd = fd
+        ctx.set_materialize_grads(False)      # an unused skip output (encoder-only nets) arrives as None in backward, not as a zero tensor
         if concat_c:
             ctot = c + concat_c
             buf = torch.empty((n, d, h, w, ctot), dtype=x.dtype, device=x.device)
@@ -714,7 +716,10 @@ class PoolSkip(Function):
         if dy is None:
             return (dskip.contiguous() if dskip is not None else None), None, None
         dy = dy.contiguous()
-        dx = torch.empty((n, d, h, w, c), dtype=x.dtype, device=x.device)
+        odd = d % ctx.fd or h % 2 or w % 2          # floor pooling (encoder-only nets): the un-pooled tail receives no pooled gradient
+        if odd and dskip is not None:
+            raise RuntimeError('ich_b200.PoolSkip: a skip connection needs spatial sizes divisible by the pooling factor')
+        dx = (torch.zeros if odd else torch.empty)((n, d, h, w, c), dtype=x.dtype, device=x.device)
         xp, xld = _rows(x)
         sp, sld = (None, 0)
         if dskip is not None:

@@ -367,3 +367,14 @@ def test_wide_head_plumbing(dry):
     out.sum().backward()
     _grads_ok(net)
     assert dry.trace.count('ich_head_fwd') == 1 and 'ich_head_dlogit' in dry.trace
+
+
+def test_encoder_floor_pooling_plumbing(dry):
+    from src.models.networks.UNet import UNet_Encoder, UNet
+    enc = UNet_Encoder(depth=3, use_3D=True, top_filter=16, midchannels_factor=1, MLP_head=[32, 8], p_dropout=0.0).train()
+    out = enc(torch.rand(1, 1, 10, 22, 18))
+    assert out.shape == (1, 8)
+    out.sum().backward()
+    _grads_ok(enc)
+    with pytest.raises(RuntimeError):                     # a decoder still needs sizes that halve exactly
+        UNet(depth=3, use_3D=True, top_filter=16, p_dropout=0.0)(torch.rand(1, 1, 10, 22, 18))

@@ -687,3 +687,25 @@ def test_wide_multiclass_head_fp32():
         out[:, 0].sum().backward()
     assert rel(out, ref) < 1e-4 and torch.equal(out.argmax(1).cpu(), ref.argmax(1))
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_encoder_floor_pooling_odd_sizes(prec):
+    """`UNet_Encoder` has no decoder, so its nn.MaxPool stages floor odd sizes (reference UNet.py:82,313) -- so does the
+    drop-in (forward pools the whole windows only, backward leaves the un-pooled tail without a pooled gradient)."""
+    from src.models.networks.UNet import UNet_Encoder
+    kw = dict(depth=3, use_3D=True, in_channels=1, top_filter=16, midchannels_factor=1, MLP_head=[32, 8], p_dropout=0.0)
+    _, sd = seeded(UNet_Encoder, kw)
+    x = torch.rand(2, 1, 10, 22, 18, generator=torch.Generator().manual_seed(8))       # 10 x 22 x 18 -> 5 x 11 x 9 -> 2 x 5 x 4
+    fwd = lambda t, p: UO.unet_encoder_forward(t, p, use_3D=True, training=True)
+    g64, _, o64 = _oracle_grads(fwd, sd, [x], lambda o: (o * o).sum(), dtype=torch.float64)
+    with config.override(precision=prec):
+        net = UNet_Encoder(**kw)
+        net.load_state_dict(sd)
+        net = net.to(DEV).train()
+        out = net(x.to(DEV))
+        (out * out).sum().backward()
+    assert rel(out, o64[0]) < (1e-4 if prec == 'fp32' else 3e-2)
+    if prec == 'fp32':
+        worst = max(rel(p.grad, g64[k]) for k, p in net.named_parameters() if not (('.conv1.bias' in k or '.conv2.bias' in k)))
+        assert worst < 5e-3, worst
