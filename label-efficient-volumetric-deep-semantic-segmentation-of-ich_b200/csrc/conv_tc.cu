@@ -36,6 +36,7 @@ struct Params {
   int cw;    // channels per K chunk: 16 (32-byte swizzled rows) for the 3x3 kernels; 16 / 32 / 64 (32 / 64 / 128-byte rows) for the 1x1
              // GEMMs (transposed conv, heads), whose stages are small and whose TMA loads were bound by the number of 32-byte requests
   int tap_cout;   // > 0: 1x1 GEMM whose K chunks come from the per-tap maps (transposed-conv data gradient), = Cout of the transposed conv
+  int issuers;    // MMA issuer warps (2 or 3): ncu shows the MMA unit only 41-62 % busy on the N = 32 / 64 layers with two -- the issue loop, not the MMA, sets the pace
   int kds;   // kd-split (3-D layers with Cout % 128 == 0): a pipeline stage holds ONE input plane and the 9 taps of ONE depth tap, so that
              // a 128-wide cout block fits (9 x 128 x 32 B = 36 KB of weights per stage instead of 27 x 64 x 32 B = 55 KB): N = 128 MMAs
              // run at the full tensor rate (64 cycles) where N = 64 ones are operand-fetch bound (48 cycles for half the work)
@@ -52,7 +53,7 @@ constexpr int MAX_STAGES = 8;    // forward kernel: runtime depth (2 for the big
 // slab kernel: warp 0 TMA, warps 1 and 2 MMA issuers (even / odd tiles), warp 3 idle, warps 4.. epilogue.  Four epilogue warps when the
 // BatchNorm statistics are fused (128 statistic registers per thread), eight otherwise (two per TMEM lane quadrant, each taking half of
 // the accumulator columns): the transposed-conv scatter epilogue (16 column chunks per tile) was bound by its four warps.
-constexpr int F_ISSUERS = 2;
+constexpr int F_ISSUERS = 2;      // default; Params::issuers (2 or 3: warps 1..3, warp 3 is otherwise idle) is what the kernel uses
 // WIDE = cout blocks of 128 with fused statistics: eight epilogue warps there too, each set keeping the statistics of its 64 columns
 template <bool STATS, bool WIDE = false> __host__ __device__ constexpr int f_epi_warps() { return (STATS && !WIDE) ? 4 : 8; }
 template <bool STATS, bool WIDE = false> __host__ __device__ constexpr int f_threads() { return 32 * (4 + f_epi_warps<STATS, WIDE>()); }
@@ -77,8 +78,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], F_ISSUERS); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], F_ISSUERS); mbar_init(&tempty_bar[a], f_epi_warps<STATS, WIDE>()); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.issuers); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], p.issuers); mbar_init(&tempty_bar[a], f_epi_warps<STATS, WIDE>()); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
@@ -133,12 +134,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp >= 1 && warp <= p.issuers) {
     // ===================================================== MMA issuers (warp-uniform loops, elected lane issues).  One warp's issue
     // loop costs more cycles per MMA (~68) than an N <= 64 MMA itself (40-48, profiles/r01_mma_rate2.txt): two warps on different SM
     // sub-partitions issue the even and the odd M tiles of every tap.
     {
-      const int ii = warp - 1;
+      const int ii = warp - 1, NI = p.issuers;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NB >> 3) << 17) | ((128u >> 4) << 24);
       // The single issuing thread is the critical resource (measured: ~130 cycles per MMA when descriptors were rebuilt
       // from scratch): keep the per-MMA work to two adds + one register pack.  Descriptor = {lo: start>>4 | LBO, hi: const}.
@@ -184,10 +185,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 uint32_t a_lo = a_lo0 + 2u * ks + (uint32_t)ii * tile16;
                 uint32_t dcol = d_tmem + (uint32_t)ii * NB;
 #pragma unroll 2
-                for (int tt = ii; tt < T; tt += F_ISSUERS) {
+                for (int tt = ii; tt < T; tt += NI) {
                   if (elect_one()) umma_bf16(dcol, pack64(a_lo, wide_hi), bdesc, idesc, accum);
-                  a_lo += F_ISSUERS * tile16;
-                  dcol += F_ISSUERS * NB;
+                  a_lo += (uint32_t)NI * tile16;
+                  dcol += (uint32_t)NI * NB;
                 }
                 accum = 1u;
               }
@@ -204,10 +205,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 uint32_t a_lo = a_kh + 2u * (uint32_t)kw + (uint32_t)ii * tile16;
                 uint32_t dcol = d_tmem + (uint32_t)ii * NB;
 #pragma unroll 2
-                for (int tt = ii; tt < T; tt += F_ISSUERS) {
+                for (int tt = ii; tt < T; tt += NI) {
                   if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, idesc, accum);
-                  a_lo += F_ISSUERS * tile16;
-                  dcol += F_ISSUERS * NB;
+                  a_lo += (uint32_t)NI * tile16;
+                  dcol += (uint32_t)NI * NB;
                 }
                 accum = 1u;
               }
@@ -495,6 +496,7 @@ static int launch_conv_tc(Plan& pl, const void* x, int x_ld, const void* wpack_b
   p.y = (bf16*)y; p.y_ld = y_ld; p.bias = bias; p.relu = relu;
   p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
   { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { static int ni = -1; if (ni < 0) { const char* e = getenv("ICH_TC_ISSUERS"); ni = (e && atoi(e) == 2) ? 2 : 3; } p.issuers = (ni == 3 && p.T >= 3) ? 3 : 2; }
   if (stat_sum) {
     ICH_REQUIRE(stat_sumsq != nullptr && p.KS == 3 && !p.up_fd, "%s: fused statistics need both buffers and a 3x3 conv", what);
     cudaMemsetAsync(stat_sum, 0, sizeof(double) * Cout, stream);

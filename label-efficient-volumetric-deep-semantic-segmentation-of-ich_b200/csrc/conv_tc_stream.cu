@@ -34,6 +34,7 @@ struct SParams {
   int relu;
   double* stat_sum;
   double* stat_sumsq;
+  int issuers;   // MMA issuer warps: 2, or 3 (warp 3 joins) when an item has >= 3 tiles
   int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA slab loads, 4 = no epilogue math / stores
   int y32;   // output rows are 32-byte aligned: 256-bit stores
 };
@@ -81,8 +82,8 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], S_ISSUERS); }
-    for (int a = 0; a < MAX_SLOTS; ++a) { mbar_init(&tfull_bar[a], S_ISSUERS); mbar_init(&tempty_bar[a], S_EPI_WARPS); }
+    for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.issuers); }
+    for (int a = 0; a < MAX_SLOTS; ++a) { mbar_init(&tfull_bar[a], p.issuers); mbar_init(&tempty_bar[a], S_EPI_WARPS); }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
   }
@@ -140,11 +141,11 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp >= 1 && warp <= p.issuers) {
     // ===================================================== MMA issuers.  The issue loop is bound by the latency of its own (uniform
     // datapath) instruction stream -- ~68 cycles per MMA measured with the MMAs themselves ablated, against 56 cycles of tensor
     // work for N = 96 -- so TWO warps on different SM sub-partitions issue the even and the odd tiles of every (plane, chunk, tap).
-    const int ii = warp - 1;
+    const int ii = warp - 1, NI = p.issuers;
     const uint32_t NB = (uint32_t)p.NB;
     const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
     const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
@@ -206,20 +207,20 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                     const uint64_t bdesc = pack64(b_tap + r_brow0, desc_hi);
                     uint32_t a_lo = a_kh + 2u * (uint32_t)kw, dcol = r_dcol0;
 #pragma unroll 2
-                    for (int tt = ii; tt < T; tt += S_ISSUERS) {
+                    for (int tt = ii; tt < T; tt += NI) {
                       if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, r_idesc0, 1u);
-                      a_lo += S_ISSUERS * tile16;
-                      dcol += S_ISSUERS * tstep;
+                      a_lo += (uint32_t)NI * tile16;
+                      dcol += (uint32_t)NI * tstep;
                     }
                   }
                   if (two_runs) {
                     const uint64_t bdesc = pack64(b_tap + r_brow1, desc_hi);
                     uint32_t a_lo = a_kh + 2u * (uint32_t)kw, dcol = r_dcol1;
 #pragma unroll 2
-                    for (int tt = ii; tt < T; tt += S_ISSUERS) {
+                    for (int tt = ii; tt < T; tt += NI) {
                       if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, r_idesc1, 1u);
-                      a_lo += S_ISSUERS * tile16;
-                      dcol += S_ISSUERS * tstep;
+                      a_lo += (uint32_t)NI * tile16;
+                      dcol += (uint32_t)NI * tstep;
                     }
                   }
                 }
@@ -465,6 +466,7 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   p.y32 = (((uintptr_t)y & 31) == 0 && y_ld % 16 == 0) ? 1 : 0;
   p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
   { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  { static int ni = -1; if (ni < 0) { const char* e = getenv("ICH_TC_STREAM_ISSUERS"); ni = (e && atoi(e) == 3) ? 3 : 2; } p.issuers = (ni == 3 && p.T >= 3) ? 3 : 2; }
   if (stat_sum) {
     ICH_REQUIRE(stat_sumsq != nullptr, "%s: fused statistics need both buffers", what);
     cudaMemsetAsync(stat_sum, 0, sizeof(double) * Cout, stream);
