@@ -13,7 +13,7 @@ PKG_ROOT = os.path.dirname(_HERE)
 REPO_ROOT = os.path.dirname(PKG_ROOT)
 CSRC = os.path.join(PKG_ROOT, 'csrc')
 HEADER = os.path.join(REPO_ROOT, 'include', 'ich_b200.h')
-LIB_PATH = os.path.join(_HERE, 'libich_b200.so')
+LIB_PATH = os.environ.get('ICH_B200_LIB') or os.path.join(_HERE, 'libich_b200.so')     # ICH_B200_LIB: an alternative build (e.g. the -DICH_TC_DEBUG ablation build of scratch/build_debug_lib.sh)
 SOURCES = ['api.cu', 'gemm_generic.cu', 'elementwise.cu', 'loss.cu', 'conv_tc.cu', 'conv_tc_stream.cu', 'conv_cin1_tc.cu', 'aux_ops.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
