@@ -368,7 +368,11 @@ Plan make_plan(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, in
   // ... but not on the smallest planes (16 x 16 at the bottleneck of cfg-3): an item is then a single M tile and the 36 KB weight stage
   // is re-fetched for 9 MMAs of work (measured: bt.c2 forward 0.051 -> 0.069 ms with the wide block)
   const bool wide = KS == 3 && wide_env && Cout % 128 == 0 && (long long)H * W >= 1024;
-  const int kds = (wide && KD == 3) ? 1 : 0;
+  // experiment (ICH_TC_KDS64=1, off by default): per-plane staging also for the 64-wide cout blocks -- smaller stages let an item take
+  // more rows, i.e. fewer weight bytes per output on the L2-bound mid-resolution layers
+  static int kds64_env = -1;
+  if (kds64_env < 0) { const char* e = getenv("ICH_TC_KDS64"); kds64_env = e ? atoi(e) : 0; }
+  const int kds = (KD == 3 && KS == 3 && (wide || (kds64_env && Cout % 64 == 0 && (long long)H * W >= 1024))) ? 1 : 0;
   const int stage_taps = kds ? 9 : taps, stage_planes = kds ? 1 : KD;
   for (int NB = (KS == 1 ? 256 : (wide ? 128 : 64)); NB >= 16; NB -= 16) {
     if (Cout % NB || (nb_must_divide && nb_must_divide % NB)) continue;
