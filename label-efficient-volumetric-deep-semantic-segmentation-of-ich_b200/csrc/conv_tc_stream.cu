@@ -35,6 +35,10 @@ struct SParams {
   double* stat_sum;
   double* stat_sumsq;
   int issuers;   // MMA issuer warps: 2, or 3 (warp 3 joins) when an item has >= 3 tiles
+  int cs;        // thread-block cluster size (1 = none).  > 1: the CTAs of a cluster work on adjacent row blocks of the SAME (sample, depth
+                 // segment, cout block) in lockstep, and the weight tile of every (plane, channel chunk) stage -- identical for all of them --
+                 // is fetched from L2 ONCE and TMA-multicast into the stage of every CTA (weights that do not fit in shared memory made
+                 // the kd-fold L2-bound on the mid-resolution layers: 55 KB per stage for 2 tiles of work)
   int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA slab loads, 4 = no epilogue math / stores
   int y32;   // output rows are 32-byte aligned: 256-bit stores
 };
@@ -69,7 +73,8 @@ __device__ __forceinline__ uint32_t s_pack_bf16x2(float lo, float hi) {
 
 template <bool STATS, int SNB>
 __global__ void __launch_bounds__(S_THREADS, 1)
-conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const SParams p) {
+conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const SParams p,
+                      const __grid_constant__ CUtensorMap map_w_lo, const __grid_constant__ CUtensorMap map_w_hi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[S_MAX_STAGES], empty_bar[S_MAX_STAGES], tfull_bar[MAX_SLOTS], tempty_bar[MAX_SLOTS], w_bar;
@@ -82,7 +87,8 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.issuers); }
+    // cluster mode: a stage is free when the issuers of EVERY CTA of the cluster have released it (the leader's multicast writes all of them)
+    for (int s = 0; s < S_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.issuers * p.cs); }
     for (int a = 0; a < MAX_SLOTS; ++a) { mbar_init(&tfull_bar[a], p.issuers); mbar_init(&tempty_bar[a], S_EPI_WARPS); }
     mbar_init(&w_bar, 1);
     fence_barrier_init();
@@ -91,6 +97,9 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const uint32_t crank = p.cs > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+  if (p.cs > 1) cluster_sync_all();          // every CTA's barriers are initialised before any peer signals them
   const uint32_t tmem_base = tmem_base_smem;
   if (warp >= 4 && warp <= 7) {   // all accumulator slots start out zero: every MMA accumulates
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
@@ -133,7 +142,16 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             else {
               mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + (p.b_resident ? 0u : p.b_bytes));
               tma_load_4d(sa, &map_x, &full_bar[stage], kc * 16, w0 - 1, h0 - 1, n * p.D + pl);
-              if (!p.b_resident) tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb_fixed * p.NB, 0);
+              if (!p.b_resident) {
+                if (p.cs == 1) tma_load_3d(sb, &map_w, &full_bar[stage], kc * 16, nb_fixed * p.NB, 0);
+                // cluster: each CTA fetches ITS SHARE of the 27 taps and multicasts it into the stage of all -- 1/cs of the L2 reads and, per
+                // CTA, 1/cs of the TMA row requests (the 32-byte rows of the 55 KB weight tile are what bounds the producer)
+                else {
+                  const int wt = (27 + p.cs - 1) / p.cs, t0 = (int)crank * wt;      // 14 / 13 taps (pair), 7 / 7 / 7 / 6 (cluster of 4)
+                  tma_load_3d_multicast(sb + (size_t)t0 * p.NB * 32, (int)crank == p.cs - 1 ? &map_w_hi : &map_w_lo, &full_bar[stage], kc * 16,
+                                        nb_fixed * p.NB, t0, cmask);
+                }
+              }
             }
           }
           __syncwarp();
@@ -227,7 +245,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               }
             }
             __syncwarp();
-            if (elect_one()) umma_commit(&empty_bar[stage]);
+            if (elect_one()) { if (p.cs > 1) umma_commit_multicast(&empty_bar[stage], cmask); else umma_commit(&empty_bar[stage]); }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -347,6 +365,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) cluster_sync_all();          // no CTA leaves while a peer may still signal its barriers / write its stages
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -433,6 +452,14 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
   p.slots = SLOTS; p.slot_shift = SLOTS == 8 ? 3 : 2;
   p.tmem_cols = cols;
   p.n_items = (long long)N * p.n_ds * p.n_rb * p.n_wb * p.n_nb;
+  // thread-block clusters with the weight stage multicast (see SParams::cs): only where the weights travel with every stage, and where
+  // consecutive CTAs are adjacent row blocks of one (sample, depth segment): one cout block, one w block, row blocks a multiple of cs
+  static int cs_env = -1;
+  if (cs_env < 0) { const char* e = getenv("ICH_TC_STREAM_CLUSTER"); cs_env = e ? atoi(e) : 0; }
+  p.cs = 1;
+  // lockstep needs the same number of processed planes in every item: one depth segment, or two full ones (each skips one halo plane)
+  const bool same_planes = p.n_ds == 1 || (p.n_ds == 2 && D % p.DS == 0);
+  if ((cs_env == 2 || cs_env == 4) && !bestRes && p.n_nb == 1 && same_planes && p.n_items % cs_env == 0 && p.n_items >= 2 * cs_env) p.cs = cs_env;
   pl.smem_bytes = best_smem;
   pl.ok = true;
   return pl;
@@ -492,6 +519,19 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(w) failed with %d", what, (int)r);
   }
+  CUtensorMap map_w_lo = map_w, map_w_hi = map_w;      // cluster mode: boxes of ceil(27 / cs) taps, and of the remainder for the last CTA
+  if (p.cs > 1) {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 27};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const int wt = (27 + p.cs - 1) / p.cs;
+    for (int half = 0; half < 2; ++half) {
+      cuuint32_t box[3] = {16, (cuuint32_t)p.NB, (cuuint32_t)(half == 0 ? wt : 27 - (p.cs - 1) * wt)};
+      CUresult r = enc(half == 0 ? &map_w_lo : &map_w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wpack_bf16), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ICH_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled(w half %d) failed with %d", what, half, (int)r);
+    }
+  }
   static bool attr_done[64] = {};   // cudaFuncSetAttribute is a per-DEVICE setting
   int attr_dev = 0; cudaGetDevice(&attr_dev);
   bool& attr_set = attr_done[attr_dev & 63];
@@ -506,8 +546,21 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   long long grid = p.n_items < ich_num_sms() ? p.n_items : ich_num_sms();
   grid = grid / p.n_nb * p.n_nb;
   if (grid < p.n_nb) grid = p.n_nb;
-  if (stat_sum && p.NB <= 32) conv_tc_stream_kernel<true, 32><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else if (stat_sum) conv_tc_stream_kernel<true, 64><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
-  else conv_tc_stream_kernel<false, 1><<<(unsigned)grid, S_THREADS, pl.smem_bytes, stream>>>(map_x, map_w, p);
+  if (p.cs > 1) grid = grid / p.cs * p.cs;       // whole clusters; n_items is a multiple of cs, so every CTA of a cluster gets the same number of items
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(S_THREADS);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.cs > 1 ? 1 : 0;
+  cudaError_t le;
+  if (stat_sum && p.NB <= 32) le = cudaLaunchKernelEx(&cfg, conv_tc_stream_kernel<true, 32>, map_x, map_w, p, map_w_lo, map_w_hi);
+  else if (stat_sum) le = cudaLaunchKernelEx(&cfg, conv_tc_stream_kernel<true, 64>, map_x, map_w, p, map_w_lo, map_w_hi);
+  else le = cudaLaunchKernelEx(&cfg, conv_tc_stream_kernel<false, 1>, map_x, map_w, p, map_w_lo, map_w_hi);
+  (void)le;
   return ich_check_launch(what);
 }

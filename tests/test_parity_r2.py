@@ -709,3 +709,18 @@ def test_encoder_floor_pooling_odd_sizes(prec):
     if prec == 'fp32':
         worst = max(rel(p.grad, g64[k]) for k, p in net.named_parameters() if not (('.conv1.bias' in k or '.conv2.bias' in k)))
         assert worst < 5e-3, worst
+
+
+def test_stream_kernel_with_cluster_multicast():
+    """Opt-in experiment (ICH_TC_STREAM=2 ICH_TC_STREAM_CLUSTER=2): the plane-streaming kernel on the mid-resolution layers with 2-CTA
+    thread-block clusters whose CTAs fetch half of the 27 weight taps each and TMA-multicast them into both stages.  The kernel variant
+    is chosen from the environment once per process, so the check runs in a child process (scratch/check_stream_cluster.py compares
+    against torch's fp32 conv on shapes with and without resident weights)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, ICH_TC_STREAM='2', ICH_TC_STREAM_CLUSTER='2')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'scratch', 'check_stream_cluster.py')], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if 'rel err' in l]
+    assert len(lines) == 8 and all(' OK ' in l for l in lines), r.stdout
+    assert all('variant 2' in l for l in lines)           # the streaming kernel really ran
