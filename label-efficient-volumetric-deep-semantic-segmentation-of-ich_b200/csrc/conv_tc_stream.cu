@@ -388,7 +388,9 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
   else return pl;
   const int PW = WB + 2;
   int NB = 0;
-  for (int c = 64; c >= 16; c -= 16)
+  static int nb_cap = -1;      // experiment: ICH_TC_STREAM_NB=32 caps the cout block (weights of a 64 -> 64 layer then stay resident, T = 4 tiles)
+  if (nb_cap < 0) { const char* e = getenv("ICH_TC_STREAM_NB"); nb_cap = e ? atoi(e) : 64; if (nb_cap < 16 || nb_cap > 64) nb_cap = 64; }
+  for (int c = nb_cap; c >= 16; c -= 16)
     if (Cout % c == 0) { NB = c; break; }
   if (!NB) return pl;
   const bool row_mode = (WB == 128);
