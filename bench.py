@@ -462,7 +462,8 @@ def main():
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf if peak_tf else None,
                 'peak_source': f'{pk_src}: {"burst" if burst else "sustained"} bf16 peak (median SM clock under load '
                                f'{clocks["sm_mhz"] if clocks else None} MHz vs max {clocks["sm_max_mhz"] if clocks else None})',
-                'traffic': None, 'traffic_note': 'per-launch DRAM bytes from ncu --set full are in profiles/ (README there), not re-measured by this run',
+                'traffic': None, 'traffic_note': 'per-launch DRAM bytes from ncu are in profiles/ (README there), not re-measured by this run',
+                'algorithmic_bytes_per_step': sum(fam[f].get('algo_bytes_per_step', 0.0) for f in profile.TENSOR_FAMILIES if f in fam),
                 'conv_ms_per_step': t_ms, 'conv_share_of_step': t_ms / (1e3 * t_prof / n_prof) if t_prof else None,
                 'algorithmic_conv_tflop_per_step': t_flop / 1e3,
                 'tensor_families': {f: {'tflops': fam[f].get('tflops'), 'frac': (fam[f].get('tflops') or 0.0) / peak_tf, 'ms_per_step': fam[f]['ms_per_step']}
@@ -471,6 +472,18 @@ def main():
                                      'launches_per_step': v['launches_per_step']}
                                  for f, v in fam.items() if f not in profile.TENSOR_FAMILIES},
                 'hbm_peak_gbs': hbm}
+
+        # DRAM bytes the same launches moved, from the committed ncu launch list of this workload (a number taken under ncu is never
+        # re-measured here; it is comparable because `achieved` sums over exactly these launches)
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'conv_dram_traffic.json')) as f:
+                tr = json.load(f).get(args.config)
+        except (OSError, ValueError):
+            tr = None
+        if tr and tr.get('batch_per_gpu') == batch and args.precision == 'bf16':
+            roof['traffic'] = tr['dram_read_bytes_per_step'] + tr['dram_write_bytes_per_step']
+            roof['traffic_note'] = ('bytes per step = dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step (the launches '
+                                    '`achieved` sums over); ' + tr['source'])
 
     cpu = None
     if rank == 0 and world == 1 and args.impl == 'b200' and not args.no_cpu_baseline:

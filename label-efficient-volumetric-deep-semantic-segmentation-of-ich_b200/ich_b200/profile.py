@@ -14,12 +14,17 @@ def _vox(a):
 
 def _conv(a, tag):
     cin = a.get('Cin', 1)
-    f = 2.0 * _vox(a) * cin * a['Cout'] * a.get('KD', 1) * a.get('KH', 3) * a.get('KW', 3)
-    return ('conv_' + (tag or 'fwd'), f, None)
+    taps = a.get('KD', 1) * a.get('KH', 3) * a.get('KW', 3)
+    f = 2.0 * _vox(a) * cin * a['Cout'] * taps
+    # DRAM bytes if every operand crosses once: input + output (data-gradient: the same two tensors the other way round; weight gradient:
+    # both read) + the weights (bf16 pack read, or the fp32 gradient written)
+    b = float(_vox(a) * (cin + a['Cout']) * _es(a) + taps * cin * a['Cout'] * (4 if tag == 'wgrad' else 2))
+    return ('conv_' + (tag or 'fwd'), f, b)
 
 
 def _convT(a, tag):
-    return ('convT', 2.0 * _vox(a) * a['Cin'] * a['Cout'] * 4 * a['FD'], None)
+    taps = 4 * a['FD']          # `_vox` = coarse voxels; the fine tensor has `taps` voxels per coarse one
+    return ('convT', 2.0 * _vox(a) * a['Cin'] * a['Cout'] * taps, float(_vox(a) * (a['Cin'] + taps * a['Cout']) * _es(a)))
 
 
 def _bw(family, fn):
@@ -94,7 +99,7 @@ def summarise(records, steps):
         a['bytes'] += by or 0.0
     out = {}
     for f, a in fam.items():
-        o = {'ms_per_step': a['ms'] / steps, 'launches_per_step': a['n'] / steps}
+        o = {'ms_per_step': a['ms'] / steps, 'launches_per_step': a['n'] / steps, 'algo_bytes_per_step': a['bytes'] / steps}
         if a['flop'] and a['ms']:
             o['tflops'] = a['flop'] / (a['ms'] * 1e-3) / 1e12
         if a['bytes'] and a['ms']:

@@ -44,10 +44,24 @@ def test_algorithmic_work_table():
         assert name in protos or name == 'ich_threshold_confusion', name
     args = dict(N=8, D=64, H=128, W=128, Cin=64, Cout=32, KD=3, KH=3, KW=3)
     fam, flop, by = profile.algo_work('ich_conv_tc_fwd_stats', args, 'fwd')
-    assert fam == 'conv_fwd' and by is None and abs(flop - 927.7e9) < 1e9                  # u2.c1 = 927.7 GFLOP
+    assert fam == 'conv_fwd' and abs(flop - 927.7e9) < 1e9                                 # u2.c1 = 927.7 GFLOP
+    assert by == 8 * 64 * 128 * 128 * (64 + 32) * 2 + 27 * 64 * 32 * 2                      # input + output once (bf16) + the weight pack
     assert profile.algo_work('ich_conv_tc_wgrad', args)[0] == 'conv_wgrad'
     fam, flop, by = profile.algo_work('ich_bn_act_bwd', dict(M=1 << 20, C=32, dtype=1))
     assert fam == 'bn_bwd' and flop is None and by == 5 * (1 << 20) * 32 * 2
     assert profile.algo_work('ich_bn_finalize', {})[0] == 'small'
-    fam, flop, _ = profile.algo_work('ich_convT2_tc_dgrad', dict(N=8, D=32, H=64, W=64, Cin=64, Cout=32, FD=2))
+    fam, flop, by = profile.algo_work('ich_convT2_tc_dgrad', dict(N=8, D=32, H=64, W=64, Cin=64, Cout=32, FD=2))
     assert fam == 'convT' and abs(flop - 34.4e9) < 0.1e9                                   # upT2 = 34.4 GFLOP
+    assert by == 8 * 32 * 64 * 64 * (64 + 8 * 32) * 2                                       # coarse tensor + the 8x larger fine one
+
+
+def test_conv_dram_traffic_file_matches_the_default_workload():
+    """`roofline.traffic` comes from a committed ncu launch list: the file must name the default workload at its per-GPU batch and sit within
+    a small factor of the algorithmic bytes (SURVEY section 8d layer table), else the number in the bench line is stale."""
+    import json
+    import bench
+    tr = json.load(open(os.path.join(ROOT, 'profiles', 'conv_dram_traffic.json')))['cfg3']
+    assert tr['batch_per_gpu'] == bench.WORKLOADS['cfg3']['batch']
+    assert os.path.exists(os.path.join(ROOT, tr['source'].split(' ')[0]))
+    total = tr['dram_read_bytes_per_step'] + tr['dram_write_bytes_per_step']
+    assert 17.5e9 < total < 1.25 * 17.5e9              # algorithmic: 17.55 GB per step (every conv operand once, fwd + dgrad + wgrad)
