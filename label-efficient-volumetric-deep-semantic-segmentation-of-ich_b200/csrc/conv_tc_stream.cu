@@ -41,6 +41,9 @@ struct SParams {
                  // the kd-fold L2-bound on the mid-resolution layers: 55 KB per stage for 2 tiles of work)
   int dbg;   // profiling ablations (ICH_TC_DBG): 1 = no MMA issue, 2 = no TMA slab loads, 4 = no epilogue math / stores
   int y32;   // output rows are 32-byte aligned: 256-bit stores
+  int cring; // 1: ONE accumulator ring of slots * T cells shared by the tiles (tile t, output plane g -> cell (slots * t + g) mod (slots * T)):
+             // the three live planes of a tile then wrap -- and its MMA splits in two -- only where the ring passes the end of the
+             // allocation, 2 of every slots * T planes instead of 2 of every `slots` (N = 96: 56 cycles unsplit, 48 + 40 split)
 };
 
 constexpr int S_THREADS = 384;      // warp 0: TMA, warps 1 and 2: MMA issuers (even / odd tiles), warp 3: idle, warps 4..11: epilogue (two per TMEM lane quadrant)
@@ -48,6 +51,7 @@ constexpr int S_EPI_WARPS = 8;
 constexpr int S_ISSUERS = 2;
 constexpr int S_MAX_STAGES = 6;
 constexpr int MAX_SLOTS = 8;          // accumulator ring: p.slots = 4 or 8 output planes (power of two)
+constexpr int S_MAX_TI = 2;           // tiles per issuer warp (T <= 4 tiles per item, >= 2 issuers)
 
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
   asm volatile(
@@ -169,7 +173,6 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     const uint32_t desc_hi = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
     const uint32_t row16 = ((uint32_t)p.PW * 32u) >> 4;
     const uint32_t tile16 = (p.row_mode ? (uint32_t)p.PW : 128u) * 2u;
-    const uint32_t tstep = (uint32_t)p.slots * NB;                      // TMEM columns between consecutive tiles
     const int T = p.T;
     int stage = 0; uint32_t phase = 0;
     long long g_base = 0;                                              // output planes completed by this CTA so far
@@ -189,23 +192,30 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             acquired = d;
           }
           tc_fence_after();
-          // The three live output planes lo..hi occupy <= 2 runs of consecutive ring slots (the ring wraps): resolve the runs ONCE per
-          // input plane -- accumulator column, instruction descriptor (N = run length * NB) and the depth-tap row offset inside a
+          // The live output planes lo..hi of a tile occupy <= 2 runs of consecutive ring cells (the ring wraps): resolve the runs ONCE per
+          // input plane and tile -- accumulator column, instruction descriptor (N = run length * NB) and the depth-tap row offset inside a
           // (kh, kw) weight group -- so that the per-tap work below is two adds and a pack per MMA.
-          uint32_t r_dcol0, r_idesc0, r_brow0, r_dcol1 = 0, r_idesc1 = 0, r_brow1 = 0;
-          bool two_runs;
+          uint32_t r_dcol0[S_MAX_TI], r_idesc0[S_MAX_TI], r_dcol1[S_MAX_TI], r_idesc1[S_MAX_TI], r_brow1[S_MAX_TI];
+          bool r_two[S_MAX_TI];
+          const int cnt = hi - lo + 1;
+          const uint32_t r_brow0 = (uint32_t)(lo - (pl - 1)) * NB * 2u;     // kd' = d - pl + 1, rows of 32 B = 2 units
           {
-            const uint32_t g0 = (uint32_t)(g_base + (lo - d0));
-            const int s0 = (int)(g0 & (uint32_t)(p.slots - 1)), cnt = hi - lo + 1;
-            const int m0 = min(cnt, p.slots - s0);
-            r_dcol0 = tmem_base + (uint32_t)s0 * NB + (uint32_t)ii * tstep;
-            r_idesc0 = idesc_base | ((((uint32_t)m0 * NB) >> 3) << 17);
-            r_brow0 = (uint32_t)(lo - (pl - 1)) * NB * 2u;                 // kd' = d - pl + 1, rows of 32 B = 2 units
-            two_runs = m0 < cnt;
-            if (two_runs) {
-              r_dcol1 = tmem_base + (uint32_t)ii * tstep;                  // wrapped: slot 0
-              r_idesc1 = idesc_base | ((((uint32_t)(cnt - m0) * NB) >> 3) << 17);
-              r_brow1 = (uint32_t)(lo + m0 - (pl - 1)) * NB * 2u;
+            const long long g0 = g_base + (lo - d0);
+            const int ring = p.cring ? p.slots * T : p.slots;               // cells per ring: shared by the tiles, or one ring per tile
+            const int o_plane = p.cring ? (int)(g0 % ring) : (int)(g0 & (p.slots - 1));
+#pragma unroll
+            for (int j = 0; j < S_MAX_TI; ++j) {
+              const int tt = ii + j * NI;
+              int base = 0, o = o_plane;
+              if (p.cring) { o += tt * p.slots; if (o >= ring) o -= ring; if (o >= ring) o %= ring; }
+              else base = tt * p.slots;
+              const int m0 = min(cnt, ring - o);
+              r_dcol0[j] = tmem_base + (uint32_t)(base + o) * NB;
+              r_idesc0[j] = idesc_base | ((((uint32_t)m0 * NB) >> 3) << 17);
+              r_two[j] = m0 < cnt;
+              r_dcol1[j] = tmem_base + (uint32_t)base * NB;                 // wrapped: first cell of the ring
+              r_idesc1[j] = idesc_base | ((((uint32_t)(cnt - m0) * NB) >> 3) << 17);
+              r_brow1[j] = (uint32_t)(lo + m0 - (pl - 1)) * NB * 2u;
             }
           }
           for (int kc = 0; kc < p.KC; ++kc) {
@@ -221,24 +231,17 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               for (int kh = 0; kh < 3; ++kh, a_kh += row16) {
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw, b_tap += 6u * NB) {
-                  {
-                    const uint64_t bdesc = pack64(b_tap + r_brow0, desc_hi);
-                    uint32_t a_lo = a_kh + 2u * (uint32_t)kw, dcol = r_dcol0;
-#pragma unroll 2
-                    for (int tt = ii; tt < T; tt += NI) {
-                      if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, r_idesc0, 1u);
+                  const uint64_t bdesc0 = pack64(b_tap + r_brow0, desc_hi);
+                  uint32_t a_lo = a_kh + 2u * (uint32_t)kw;
+#pragma unroll
+                  for (int j = 0; j < S_MAX_TI; ++j) {
+                    if (ii + j * NI < T) {
+                      const uint64_t adesc = pack64(a_lo, desc_hi);
+                      if (elect_one()) umma_bf16(r_dcol0[j], adesc, bdesc0, r_idesc0[j], 1u);
+                      if (r_two[j]) {
+                        if (elect_one()) umma_bf16(r_dcol1[j], adesc, pack64(b_tap + r_brow1[j], desc_hi), r_idesc1[j], 1u);
+                      }
                       a_lo += (uint32_t)NI * tile16;
-                      dcol += (uint32_t)NI * tstep;
-                    }
-                  }
-                  if (two_runs) {
-                    const uint64_t bdesc = pack64(b_tap + r_brow1, desc_hi);
-                    uint32_t a_lo = a_kh + 2u * (uint32_t)kw, dcol = r_dcol1;
-#pragma unroll 2
-                    for (int tt = ii; tt < T; tt += NI) {
-                      if (elect_one()) umma_bf16(dcol, pack64(a_lo, desc_hi), bdesc, r_idesc1, 1u);
-                      a_lo += (uint32_t)NI * tile16;
-                      dcol += (uint32_t)NI * tstep;
                     }
                   }
                 }
@@ -306,6 +309,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       for (int d = d0; d < dend; ++d) {
         const long long g = g_base + (d - d0);
         const int slot = (int)(g & (p.slots - 1));
+        const int ring = p.slots * p.T, gm = (int)(g % ring);
         mbar_wait(&tfull_bar[slot], (uint32_t)((g >> p.slot_shift) & 1));
         tc_fence_after();
         for (int tt = eset; tt < p.T; tt += 2) {
@@ -314,7 +318,7 @@ conv_tc_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           const bool valid = (pos < p.WB) && (r < p.R) && (h0 + r < p.H) && (w0 + pos < p.W) && plain;
           const long long vox = (((long long)n * p.D + d) * p.H + (h0 + r)) * p.W + (w0 + pos);
           bf16* yrow = p.y + vox * p.y_ld + n0;
-          const uint32_t taddr = lane_base + (uint32_t)((tt * p.slots + slot) * p.NB);
+          const uint32_t taddr = lane_base + (uint32_t)((p.cring ? (tt * p.slots + gm) % ring : tt * p.slots + slot) * p.NB);
           if ((p.NB & 31) == 0) {
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {       // compile-time column offsets: the statistics stay in registers
@@ -402,7 +406,7 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
   static int slots_env = -1;
   if (slots_env < 0) { const char* e = getenv("ICH_TC_STREAM_SLOTS"); slots_env = e ? atoi(e) : 16; }
   const int SLOTS = (slots_env >= 8 && NB <= slots_env && NB <= 32) ? 8 : 4;
-  const int Tmax = 512 / (SLOTS * NB);
+  const int Tmax = 512 / (SLOTS * NB) < 2 * S_MAX_TI ? 512 / (SLOTS * NB) : 2 * S_MAX_TI;
   const uint32_t b_bytes = 27u * NB * 32u;
   int bestR = 0, bestT = 0, bestStages = 0, bestRes = 0;
   size_t best_smem = 0;
@@ -496,6 +500,12 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
   { const char* e = getenv("ICH_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   { static int ni = -1; if (ni < 0) { const char* e = getenv("ICH_TC_STREAM_ISSUERS"); ni = (e && atoi(e) == 3) ? 3 : 2; } p.issuers = (ni == 3 && p.T >= 3) ? 3 : 2; }
+  // Shared ring where it measured faster (profiles/r02x_stream_cring.txt): 4-slot plans with cout blocks of 32 (u2.c1 / u2.c2 / d0.c2 forward
+  // 4-5 %, d1.c2 data-gradient 10 %); the 8-slot ring of the 16-wide blocks and the 2-tile items of the 64-wide blocks were 2-5 % slower with
+  // it.  ICH_TC_STREAM_CRING=0: never, =2: always (tests).
+  { static int cr = -1; if (cr < 0) { const char* e = getenv("ICH_TC_STREAM_CRING"); cr = e ? atoi(e) : 1; if (cr < 0 || cr > 2) cr = 1; }
+    p.cring = cr == 2 || (cr == 1 && p.slots == 4 && p.NB <= 32) ? 1 : 0; }
+  ICH_REQUIRE((p.T + p.issuers - 1) / p.issuers <= S_MAX_TI, "%s: %d tiles per item exceed the issuer's tile table", what, p.T);
   if (stat_sum) {
     ICH_REQUIRE(stat_sumsq != nullptr, "%s: fused statistics need both buffers", what);
     cudaMemsetAsync(stat_sum, 0, sizeof(double) * Cout, stream);

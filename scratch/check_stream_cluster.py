@@ -9,7 +9,7 @@ config.set(precision='bf16')
 torch.backends.cudnn.allow_tf32 = False
 print('env', {k: v for k, v in os.environ.items() if k.startswith('ICH_TC')})
 SHAPES = [(1, 4, 12, 64, 64, 64), (2, 6, 24, 64, 128, 64), (1, 5, 8, 64, 64, 32), (8, 32, 64, 64, 64, 64), (8, 32, 64, 64, 128, 64), (8, 32, 64, 64, 32, 32),
-          (8, 32, 64, 64, 64, 32), (8, 16, 32, 32, 128, 128)]
+          (8, 32, 64, 64, 64, 32), (8, 16, 32, 32, 128, 128), (1, 20, 16, 128, 32, 16), (2, 9, 12, 128, 16, 32)]
 for n, d, h, w, cin, cout in SHAPES:
     g = torch.Generator(device='cuda').manual_seed(1)
     x = torch.randn(n, d, h, w, cin, device='cuda', generator=g).bfloat16()

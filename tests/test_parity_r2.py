@@ -722,5 +722,20 @@ def test_stream_kernel_with_cluster_multicast():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'scratch', 'check_stream_cluster.py')], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if 'rel err' in l]
-    assert len(lines) == 8 and all(' OK ' in l for l in lines), r.stdout
+    assert len(lines) == 10 and all(' OK ' in l for l in lines), r.stdout
     assert all('variant 2' in l for l in lines)           # the streaming kernel really ran
+
+
+@pytest.mark.parametrize('cring', ['0', '2'])
+def test_stream_kernel_accumulator_ring_variants(cring):
+    """The plane-streaming kernel keeps its accumulators either in one 4- / 8-slot ring per tile or in ONE ring shared by the tiles of an
+    item (fewer split MMAs; default only for cout blocks of 32).  Both layouts on every plan family -- cout blocks of 16 (8-slot ring), 32
+    and 64, row and flat tiling, one and several depth segments -- against torch's fp32 conv, in a child process (the switch is read once)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, ICH_TC_STREAM='2', ICH_TC_STREAM_CRING=cring)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'scratch', 'check_stream_cluster.py')], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if 'rel err' in l]
+    assert len(lines) == 10 and all(' OK ' in l for l in lines), r.stdout
+    assert all('variant 2' in l for l in lines)
