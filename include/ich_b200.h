@@ -57,6 +57,10 @@ int ich_conv_tc_variant(int N, int D, int H, int W, int Cin, int Cout, int KD, i
 /* host-only: the tiling the slab kernel picks for a shape -- out[0..9] = cout block, rows per slab, M tiles per item, accumulator sets,
  * pipeline stages, kd-split, dynamic shared memory bytes, TMEM columns, K chunk width, work items; returns non-zero if unsupported */
 int ich_conv_tc_plan_info(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW, long long* out);
+/* host-only: the tiling the plane-streaming kernel (3x3x3) picks -- out[0..9] = cout block, rows per item, M tiles per item, accumulator
+ * ring slots per tile, pipeline stages, weights resident in shared memory, dynamic shared memory bytes, TMEM columns, one ring shared by
+ * the tiles (1) or one ring per tile (0), work items; returns non-zero if the shape is not one the kernel takes                      */
+int ich_conv_tc_stream_plan_info(int N, int D, int H, int W, int Cin, int Cout, long long* out);
 int ich_conv_tc_fwd(const void* x, int x_ld, const void* wpack_bf16, const float* bias, void* y, int y_ld, int N, int D, int H, int W,
                     int Cin, int Cout, int KD, int KH, int KW, int relu, void* stream);
 /* same, with the BatchNorm batch statistics (fp64 per-channel sum / sum of squares of the stored outputs) fused into the epilogue */

@@ -471,7 +471,22 @@ SPlan make_splan(int N, int D, int H, int W, int Cin, int Cout) {
   return pl;
 }
 
+int stream_shared_ring(const SParams& p) {
+  static int cr = -1;
+  if (cr < 0) { const char* e = getenv("ICH_TC_STREAM_CRING"); cr = e ? atoi(e) : 1; if (cr < 0 || cr > 2) cr = 1; }
+  return cr == 2 || (cr == 1 && p.slots == 4 && p.NB <= 32) ? 1 : 0;
+}
+
 }  // namespace
+
+extern "C" int ich_conv_tc_stream_plan_info(int N, int D, int H, int W, int Cin, int Cout, long long* out) {
+  SPlan pl = make_splan(N, D, H, W, Cin, Cout);
+  if (!pl.ok) return 1;
+  const SParams& p = pl.p;
+  out[0] = p.NB; out[1] = p.R; out[2] = p.T; out[3] = p.slots; out[4] = p.stages; out[5] = p.b_resident; out[6] = (long long)pl.smem_bytes;
+  out[7] = p.tmem_cols; out[8] = stream_shared_ring(p); out[9] = p.n_items;
+  return 0;
+}
 
 // Called by conv_tc.cu's entry points (ich_conv_tc_variant decides which kernel a shape uses).
 bool ich_stream_eligible(int N, int D, int H, int W, int Cin, int Cout, int KD, int KH, int KW) {
@@ -503,8 +518,7 @@ int ich_stream_launch(const void* x, int x_ld, const void* wpack_bf16, const flo
   // Shared ring where it measured faster (profiles/r02x_stream_cring.txt): 4-slot plans with cout blocks of 32 (u2.c1 / u2.c2 / d0.c2 forward
   // 4-5 %, d1.c2 data-gradient 10 %); the 8-slot ring of the 16-wide blocks and the 2-tile items of the 64-wide blocks were 2-5 % slower with
   // it.  ICH_TC_STREAM_CRING=0: never, =2: always (tests).
-  { static int cr = -1; if (cr < 0) { const char* e = getenv("ICH_TC_STREAM_CRING"); cr = e ? atoi(e) : 1; if (cr < 0 || cr > 2) cr = 1; }
-    p.cring = cr == 2 || (cr == 1 && p.slots == 4 && p.NB <= 32) ? 1 : 0; }
+  p.cring = stream_shared_ring(p);
   ICH_REQUIRE((p.T + p.issuers - 1) / p.issuers <= S_MAX_TI, "%s: %d tiles per item exceed the issuer's tile table", what, p.T);
   if (stat_sum) {
     ICH_REQUIRE(stat_sumsq != nullptr, "%s: fused statistics need both buffers", what);

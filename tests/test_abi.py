@@ -156,3 +156,29 @@ def test_slab_kernel_planner_limits():
             assert nb == 128 and kds == (1 if kd == 3 else 0), (cin, cout, kd, nb, kds)
         else:
             assert nb <= 64 and kds == 0
+
+
+def test_stream_kernel_planner_limits():
+    """Host-only planner of the plane-streaming kernel (ich_conv_tc_stream_plan_info): on every 3x3x3 shape it can be given -- the
+    full-resolution layers of cfg-3 / cfg-5 in both directions, the mid-resolution layers it takes under ICH_TC_STREAM=2, flat tiling
+    (W < 128), short volumes -- the accumulator ring must fit the 512 TMEM columns, an item must not have more tiles than the two issuer
+    warps' tile tables hold, shared memory <= 227 KB, >= 2 stages; the ring shared by the tiles is planned exactly for cout blocks of 32
+    (where it measured faster), and Cin / Cout that are not multiples of 16 are refused."""
+    l = _lib.lib()
+    shapes = [(8, 64, 128, 128, 16, 32), (8, 64, 128, 128, 32, 16), (8, 64, 128, 128, 64, 32), (8, 64, 128, 128, 32, 64), (8, 64, 128, 128, 32, 32),
+              (4, 32, 128, 128, 64, 32), (1, 4, 8, 128, 16, 16), (8, 32, 64, 64, 32, 64), (8, 32, 64, 64, 64, 32), (8, 32, 64, 64, 64, 64),
+              (8, 32, 64, 64, 128, 64), (8, 16, 32, 32, 128, 128), (2, 20, 12, 256, 32, 32), (1, 5, 7, 40, 48, 48)]
+    for n, d, h, w, cin, cout in shapes:
+        out = (ctypes.c_longlong * 10)()
+        rc = l.ich_conv_tc_stream_plan_info(n, d, h, w, cin, cout, ctypes.cast(out, ctypes.c_void_p))
+        assert rc == 0, (n, d, h, w, cin, cout)
+        nb, r, t, slots, stages, resident, smem, tmem, cring, items = list(out)
+        assert cout % nb == 0 and nb in (16, 32, 48, 64) and slots in (4, 8)
+        assert t * slots * nb <= 512 and tmem <= 512 and t <= 4 and 1 <= r <= h
+        assert smem <= 227 * 1024 and stages >= 2 and items > 0
+        assert cring == (1 if (nb <= 32 and slots == 4) else 0), (nb, slots, cring)
+        if cin * 27 * nb * 2 <= 96 * 1024:
+            assert resident == 1                      # small weight blocks stay in shared memory for the CTA's lifetime
+    out = (ctypes.c_longlong * 10)()
+    for bad in ((8, 64, 128, 128, 8, 32), (8, 64, 128, 128, 32, 24), (8, 2, 128, 128, 32, 32), (8, 64, 128, 192, 32, 32)):
+        assert l.ich_conv_tc_stream_plan_info(*bad, ctypes.cast(out, ctypes.c_void_p)) != 0, bad
