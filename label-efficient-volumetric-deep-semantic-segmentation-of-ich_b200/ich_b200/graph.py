@@ -75,7 +75,12 @@ class GraphedStep:
                 return self.step_fn(*inputs)
             if not self._capture(inputs):  # capturing does not execute: fall through to the first replay on these inputs
                 return self.step_fn(*inputs)
+        if len(inputs) != len(self.static_in):
+            raise RuntimeError(f'ich_b200.GraphedStep: captured with {len(self.static_in)} inputs, called with {len(inputs)}')
         for s, t in zip(self.static_in, inputs):
+            if s.shape != t.shape or s.dtype != t.dtype:       # copy_ would broadcast / cast silently: a replay only fits the captured shapes
+                raise RuntimeError(f'ich_b200.GraphedStep: captured for inputs of {tuple(s.shape)} {s.dtype}, called with {tuple(t.shape)} {t.dtype} '
+                                   '(a partial last batch? use drop_last=True as the reference loaders do, or run that step eagerly)')
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
         self.graph.replay()

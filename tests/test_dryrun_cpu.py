@@ -335,6 +335,27 @@ def test_graphed_step_needs_fresh_optimizer():
         GraphedStep(lambda x: x, opt2)
 
 
+def test_graphed_step_refuses_other_shapes():
+    """A replay only fits the shapes it was captured for; `copy_` into the static inputs would broadcast a smaller batch silently."""
+    from ich_b200.graph import GraphedStep
+
+    class FakeGraph:
+        replays = 0
+
+        def replay(self):
+            FakeGraph.replays += 1
+    step = GraphedStep(lambda x: x)
+    step.graph, step.static_in, step.static_out = FakeGraph(), [torch.zeros(4, 3)], 'out'
+    assert step(torch.ones(4, 3)) == 'out' and FakeGraph.replays == 1 and float(step.static_in[0].sum()) == 12.0
+    with pytest.raises(RuntimeError, match='captured for inputs'):
+        step(torch.ones(1, 3))              # broadcastable: must not be copied in
+    with pytest.raises(RuntimeError, match='captured for inputs'):
+        step(torch.ones(4, 3, dtype=torch.float64))
+    with pytest.raises(RuntimeError, match='captured with 1 inputs'):
+        step(torch.ones(4, 3), torch.ones(4, 3))
+    assert FakeGraph.replays == 1
+
+
 def test_padded_mid_channels_plumbing(dry):
     """top_filter = 16 nets with midchannels_factor = 2 (BASELINE.json configs[0]): the 8-channel mid tensor of the first block is carried
     zero-padded to 16 channels (tcgen05 granularity); every parameter still receives a gradient of its own shape, running statistics
