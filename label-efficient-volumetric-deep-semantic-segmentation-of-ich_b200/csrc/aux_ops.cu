@@ -69,7 +69,7 @@ int stage_launch(const void* src, void* dst, int dtype, long long M, float a, fl
 
 // ---------------------------------------------------------------------------------------------------------- window gather / scatter
 // Volume [D][H][W] (one channel), windows [nw][wd][wh][ww]; starts[nw][3] = (d0, h0, w0).  Voxels of a window that fall outside the
-// volume (window larger than the volume along an axis) read as 0 / are not written.
+// volume (window larger than the volume along an axis, or a corner outside it) read as 0 / are not written.
 template <typename T>
 __global__ void __launch_bounds__(256) window_gather_kernel(const T* __restrict__ vol, int D, int H, int W, const int* __restrict__ starts, int wd,
                                                             int wh, int ww, T* __restrict__ out, long long total) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) window_gather_kernel(const T* __restrict_
     const int x = (int)(r % ww); r /= ww;
     const int y = (int)(r % wh); const int z = (int)(r / wh);
     const int d = starts[3 * n] + z, h = starts[3 * n + 1] + y, w = starts[3 * n + 2] + x;
-    out[i] = (d < D && h < H && w < W) ? vol[((long long)d * H + h) * W + w] : from_f32<T>(0.f);
+    out[i] = ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) ? vol[((long long)d * H + h) * W + w] : from_f32<T>(0.f);
   }
 }
 
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) window_scatter_kernel(const float* __rest
     const int x = (int)(r % ww); r /= ww;
     const int y = (int)(r % wh); const int z = (int)(r / wh);
     const int d = starts[3 * n] + z, h = starts[3 * n + 1] + y, w = starts[3 * n + 2] + x;
-    if (d >= D || h >= H || w >= W) continue;
+    if ((unsigned)d >= (unsigned)D || (unsigned)h >= (unsigned)H || (unsigned)w >= (unsigned)W) continue;      // also rejects negative corners
     const long long v = ((long long)d * H + h) * W + w;
     const float val = p[i];
     if (mode == 0) {
