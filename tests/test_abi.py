@@ -182,3 +182,29 @@ def test_stream_kernel_planner_limits():
     out = (ctypes.c_longlong * 10)()
     for bad in ((8, 64, 128, 128, 8, 32), (8, 64, 128, 128, 32, 24), (8, 2, 128, 128, 32, 32), (8, 64, 128, 192, 32, 32)):
         assert l.ich_conv_tc_stream_plan_info(*bad, ctypes.cast(out, ctypes.c_void_p)) != 0, bad
+
+
+def test_shared_accumulator_ring_invariants():
+    """Model of the streaming kernel's shared accumulator ring (conv_tc_stream.cu, SParams::cring): tile t keeps output plane g in cell
+    (slots * t + g) mod (slots * T).  While plane g is the newest acquired one, the planes g - slots + 1 .. g of every tile are alive
+    (three accumulating, the rest draining): no two alive (tile, plane) pairs may share a cell, the cell a tile takes for a new plane must be
+    the one plane g - slots of its neighbour tile has left (that is what the per-plane `tempty` barrier guarantees), and the three live
+    planes of a tile straddle the end of the ring -- the MMA splits in two -- for exactly 2 of every slots * T planes (per-tile rings: 2 of
+    every `slots`)."""
+    for slots, T in ((4, 4), (4, 3), (4, 2), (4, 1), (8, 4), (8, 2)):
+        ring = slots * T
+        cell = lambda t, g: (slots * t + g) % ring                                    # noqa: E731
+        splits = [0] * T
+        for g in range(slots, slots + 6 * ring):                                      # six whole turns of the ring
+            alive = {}
+            for t in range(T):
+                for q in range(g - slots + 1, g + 1):
+                    c = cell(t, q)
+                    assert c not in alive, (slots, T, g, t, q, alive[c])
+                    alive[c] = (t, q)
+            for t in range(T):
+                assert cell(t, g) == cell((t + 1) % T, g - slots)                         # freed by the neighbour's plane g - slots
+                lo = g - 2                                                               # live window lo .. g (three planes)
+                if cell(t, lo) + 3 > ring:
+                    splits[t] += 1
+        assert splits == [12] * T, (slots, T, splits)                                 # 2 per turn and tile
